@@ -1,0 +1,239 @@
+// K1: depth image -> compacted point cloud.
+// Replaces utils/utils.py:21-45 (depth_to_voxel), utils/utils.py:48-76 (depth_to_voxel_ld) and
+// the per-frame list comprehension of reconstruct.py:336-354, for a whole batch of frames.
+//
+// HBM-bound: 2 B read per pixel (uint16), 24/32 B written per valid point.  Three launches:
+//   bp_count   per 2048-pixel tile: number of pixels whose z = (int16)d * zscale is non-zero
+//   bp_scan    one CTA: exclusive scan of all tile counts (frame-major, so the result is the
+//              global output position of every tile, and of every frame)
+//   bp_write   per tile: recompute, ballot-rank inside the tile, coalesced stores
+// The tile is walked in rounds of 256 consecutive pixels so that consecutive threads read
+// consecutive pixels and, after compaction, write consecutive points.
+#include "common.cuh"
+
+namespace r3d {
+
+constexpr int BP_THREADS = 256;
+constexpr int BP_ROUNDS = 8;
+constexpr int BP_TILE = BP_THREADS * BP_ROUNDS;
+
+template <typename T> struct DepthTraits;
+template <> struct DepthTraits<uint16_t> {
+    __device__ static double as_double(uint16_t v) { return (double)v; }
+    __device__ static double z_of(uint16_t v) { return (double)(int16_t)v; }   // astype(int16): wraps
+};
+template <> struct DepthTraits<float> {
+    __device__ static double as_double(float v) { return (double)v; }
+    // astype(int16) on a float truncates toward zero (x86: cvtt to int32, low 16 bits kept)
+    __device__ static double z_of(float v) { return (double)(int16_t)(int32_t)v; }
+};
+template <> struct DepthTraits<double> {
+    __device__ static double as_double(double v) { return v; }
+    __device__ static double z_of(double v) { return (double)(int16_t)(int32_t)v; }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(BP_THREADS)
+bp_count(const T* __restrict__ depth, int hw, int tiles_per_frame, double zscale, int32_t* __restrict__ tile_count) {
+    const int frame = blockIdx.y;
+    const int tile = blockIdx.x;
+    const T* d = depth + (size_t)frame * hw;
+    const int base = tile * BP_TILE;
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < BP_ROUNDS; r++) {
+        int px = base + r * BP_THREADS + threadIdx.x;
+        if (px < hw) {
+            double z = DepthTraits<T>::z_of(d[px]) * zscale;
+            c += (z != 0.0);
+        }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int s[BP_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+#pragma unroll
+        for (int w = 0; w < BP_THREADS / 32; w++) t += s[w];
+        tile_count[(size_t)frame * tiles_per_frame + tile] = t;
+    }
+}
+
+// Exclusive scan of n int32 values by one CTA of 1024 threads; writes frame offsets as well.
+__global__ void __launch_bounds__(1024)
+bp_scan(const int32_t* __restrict__ tile_count, int32_t* __restrict__ tile_base, int n, int tiles_per_frame,
+        int frames, int32_t* __restrict__ frame_offsets) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < n; start += 1024) {
+        int i = start + threadIdx.x;
+        int v = (i < n) ? tile_count[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+            int ws = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += y;
+            }
+            warp_tot[lane] = ws - w;   // exclusive over warps
+        }
+        __syncthreads();
+        int excl = carry + warp_tot[warp] + x - v;
+        if (i < n) {
+            tile_base[i] = excl;
+            if (i % tiles_per_frame == 0) frame_offsets[i / tiles_per_frame] = excl;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) frame_offsets[frames] = carry;
+}
+
+template <typename T, int MODE, int LAYOUT>
+__global__ void __launch_bounds__(BP_THREADS)
+bp_write(const T* __restrict__ depth, int hw, int width, int tiles_per_frame, double fx, double fy, double cx,
+         double cy, double zscale, const int32_t* __restrict__ tile_base, const int32_t* __restrict__ frame_offsets,
+         void* __restrict__ out) {
+    const int frame = blockIdx.y;
+    const int tile = blockIdx.x;
+    const T* d = depth + (size_t)frame * hw;
+    const int base = tile * BP_TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = BP_THREADS / 32;
+
+    __shared__ int cnt[BP_ROUNDS * NW];   // [round][warp] valid counts -> exclusive offsets
+
+    T raw[BP_ROUNDS];
+    unsigned ballots[BP_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < BP_ROUNDS; r++) {
+        int px = base + r * BP_THREADS + threadIdx.x;
+        bool ok = false;
+        raw[r] = T(0);
+        if (px < hw) {
+            raw[r] = d[px];
+            ok = (DepthTraits<T>::z_of(raw[r]) * zscale) != 0.0;
+        }
+        ballots[r] = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) cnt[r * NW + warp] = __popc(ballots[r]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // 64 counts, two per lane, exclusive scan in (round, warp) order
+        int a = cnt[2 * lane], b = cnt[2 * lane + 1];
+        int s = a + b, x = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        int excl = x - s;
+        cnt[2 * lane] = excl;
+        cnt[2 * lane + 1] = excl + a;
+    }
+    __syncthreads();
+
+    const int out_tile = tile_base[(size_t)frame * tiles_per_frame + tile];
+    const int frame_first = frame_offsets[frame];
+#pragma unroll
+    for (int r = 0; r < BP_ROUNDS; r++) {
+        const unsigned bal = ballots[r];
+        if (!((bal >> lane) & 1u)) continue;
+        const int px = base + r * BP_THREADS + threadIdx.x;
+        const int pos = out_tile + cnt[r * NW + warp] + __popc(bal & ((1u << lane) - 1u));
+        const int v = px / width, u = px - v * width;
+        const double dv = DepthTraits<T>::as_double(raw[r]);
+        const double z = DepthTraits<T>::z_of(raw[r]) * zscale;
+        double x, y;
+        if (MODE == R3D_BP_PINHOLE) {
+            // ((u - cx) * d) / fx, in this order, IEEE double: bit-exact with utils/utils.py:72
+            x = __ddiv_rn(__dmul_rn((double)u - cx, dv), fx);
+            y = __ddiv_rn(__dmul_rn((double)v - cy, dv), fy);
+        } else {
+            x = (double)u;
+            y = (double)v;
+        }
+        if (LAYOUT == R3D_POINTS_XYZ) {
+            double* o = (double*)out + (size_t)pos * 3;
+            o[0] = x; o[1] = y; o[2] = z;
+        } else if (LAYOUT == R3D_POINTS_XYZW) {
+            store_point((Point4*)out + pos, x, y, z, pos - frame_first);
+        } else {
+            ((float4*)out)[pos] = make_float4((float)x, (float)y, (float)z, 1.0f);
+        }
+    }
+}
+
+template <typename T>
+static int bp_dispatch(const T* depth, int frames, int height, int width, int mode, double fx, double fy, double cx,
+                       double cy, double zscale, int layout, void* out, int32_t* out_offsets, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+    const int hw = height * width;
+    const int tiles = (hw + BP_TILE - 1) / BP_TILE;
+    Arena a(ws, ws_bytes);
+    int32_t* tile_count = a.take<int32_t>((size_t)frames * tiles);
+    int32_t* tile_base = a.take<int32_t>((size_t)frames * tiles);
+    if (!a.ok) return R3D_ERR_WORKSPACE;
+    dim3 grid(tiles, frames);
+    R3D_LAUNCH((bp_count<T>), grid, BP_THREADS, 0, st, depth, hw, tiles, zscale, tile_count);
+    R3D_LAUNCH(bp_scan, 1, 1024, 0, st, tile_count, tile_base, frames * tiles, tiles, frames, out_offsets);
+#define BP_CASE(M, L)                                                                                            \
+    if (mode == M && layout == L) {                                                                              \
+        R3D_LAUNCH((bp_write<T, M, L>), grid, BP_THREADS, 0, st, depth, hw, width, tiles, fx, fy, cx, cy,        \
+                   zscale, tile_base, out_offsets, out);                                                         \
+        return R3D_OK;                                                                                           \
+    }
+    BP_CASE(R3D_BP_PIXEL, R3D_POINTS_XYZ)
+    BP_CASE(R3D_BP_PIXEL, R3D_POINTS_XYZW)
+    BP_CASE(R3D_BP_PIXEL, R3D_POINTS_XYZW_F32)
+    BP_CASE(R3D_BP_PINHOLE, R3D_POINTS_XYZ)
+    BP_CASE(R3D_BP_PINHOLE, R3D_POINTS_XYZW)
+    BP_CASE(R3D_BP_PINHOLE, R3D_POINTS_XYZW_F32)
+#undef BP_CASE
+    return R3D_ERR_INVALID;
+}
+
+}  // namespace r3d
+
+extern "C" size_t r3d_backproject_workspace_bytes(int frames, int height, int width) {
+    if (frames <= 0 || height <= 0 || width <= 0) return 0;
+    const size_t tiles = ((size_t)height * width + r3d::BP_TILE - 1) / r3d::BP_TILE;
+    return 2 * r3d::align_up((size_t)frames * tiles * sizeof(int32_t), 256) + 256;
+}
+
+extern "C" int r3d_backproject(const void* depth, int depth_dtype, int frames, int height, int width, int mode,
+                               double fx, double fy, double cx, double cy, double zscale, int out_layout,
+                               void* out_points, int32_t* out_offsets, void* workspace, size_t workspace_bytes,
+                               void* stream) {
+    if (!depth || !out_points || !out_offsets || frames <= 0 || height <= 0 || width <= 0) return R3D_ERR_INVALID;
+    if ((int64_t)frames * height * width > 0x7fffffffll) return R3D_ERR_INVALID;
+    if (frames > 65535) return R3D_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (depth_dtype) {
+        case R3D_DEPTH_U16:
+            return r3d::bp_dispatch((const uint16_t*)depth, frames, height, width, mode, fx, fy, cx, cy, zscale,
+                                    out_layout, out_points, out_offsets, workspace, workspace_bytes, st);
+        case R3D_DEPTH_F32:
+            return r3d::bp_dispatch((const float*)depth, frames, height, width, mode, fx, fy, cx, cy, zscale,
+                                    out_layout, out_points, out_offsets, workspace, workspace_bytes, st);
+        case R3D_DEPTH_F64:
+            return r3d::bp_dispatch((const double*)depth, frames, height, width, mode, fx, fy, cx, cy, zscale,
+                                    out_layout, out_points, out_offsets, workspace, workspace_bytes, st);
+        default:
+            return R3D_ERR_INVALID;
+    }
+}

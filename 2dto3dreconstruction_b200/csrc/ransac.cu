@@ -1,0 +1,337 @@
+// K4: RANSAC hypothesis scoring.
+//  K4A r3d_ransac2d_score: the body of q9.ransac_loop's hypothesis loop
+//      (utils/homography_utils/q9.py:169-191) for every hypothesis at once:
+//      q9.py:52-69 get_transformed_points, q9.py:129-144 make_binned_array (as a CSR cell table
+//      with the reference's [int(r)-1][int(c)-1] negative-index wrap) and q9.py:92-127 get_ssd_v2.
+//      The reference's sequential "first keypoint to claim j wins" rule is evaluated in parallel:
+//      every keypoint i finds its windowed first-minimum j*(i); a claim succeeds iff i is the
+//      smallest claimant of j*, which is exactly what the sequential loop accepts.
+//  K4B r3d_ransac3d_score: inlier counts of 4x4 rigid/affine hypotheses over 3-D correspondences.
+// All scoring arithmetic is fp64 so that threshold and truncation decisions match NumPy.
+#include "common.cuh"
+
+namespace r3d {
+
+constexpr int RS2_THREADS = 256;
+
+struct Ransac2dWs {
+    int32_t* cell_of;      // [n2] cell id of every image-2 keypoint (or -1 when out of range)
+    int32_t* cell_start;   // [h*w + 1]
+    int32_t* items;        // [n2]
+    int32_t* first_i;      // [n_hyp][n2]
+    int32_t* jstar;        // [n_hyp][n1]
+    double* ssd;           // [n_hyp][n1]
+    int32_t* err;          // [1] build error flag
+};
+
+static void ransac2d_layout(Ransac2dWs& w, Arena& a, int n_hyp, int n1, int n2, int h, int wd) {
+    w.cell_of = a.take<int32_t>((size_t)n2);
+    w.cell_start = a.take<int32_t>((size_t)h * wd + 1);
+    w.items = a.take<int32_t>((size_t)n2);
+    w.first_i = a.take<int32_t>((size_t)n_hyp * n2);
+    w.jstar = a.take<int32_t>((size_t)n_hyp * n1);
+    w.ssd = a.take<double>((size_t)n_hyp * n1);
+    w.err = a.take<int32_t>(1);
+}
+
+// Python int(float): truncation toward zero.  Clamped so the cast is defined; the clamp range is far
+// outside any image, so window arithmetic on the clamped value gives the same (empty) ranges.
+__device__ __forceinline__ int py_int(double x) {
+    x = fmin(fmax(x, -1.0e9), 1.0e9);
+    return (int)x;   // C cast truncates toward zero
+}
+
+__global__ void r2_cells_kernel(const double* __restrict__ kp2, int n2, int h, int w, Ransac2dWs ws) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) *ws.err = 0;
+    if (j >= n2) return;
+    const double pr = kp2[2 * j], pc = kp2[2 * j + 1];
+    int cell = -1;
+    if (isfinite(pr) && isfinite(pc)) {
+        const int r = py_int(pr) - 1, c = py_int(pc) - 1;
+        // Python list indexing: -len <= index < len, negative wraps (q9.py:142)
+        if (r >= -h && r < h && c >= -w && c < w) cell = ((r + h) % h) * w + ((c + w) % w);
+    }
+    ws.cell_of[j] = cell;
+}
+
+// One CTA: histogram of cells -> exclusive scan -> stable fill (ascending j inside a cell).
+__global__ void __launch_bounds__(1024)
+r2_csr_kernel(int n2, int n_cells, Ransac2dWs ws) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = threadIdx.x; c <= n_cells; c += 1024) ws.cell_start[c] = 0;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n2; j += 1024) {
+        const int c = ws.cell_of[j];
+        if (c < 0) atomicExch(ws.err, 1); else atomicAdd(&ws.cell_start[c], 1);
+    }
+    __syncthreads();
+    for (int start = 0; start <= n_cells; start += 1024) {
+        const int i = start + threadIdx.x;
+        const int v = (i <= n_cells) ? ws.cell_start[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int t = warp_tot[lane], ts = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(0xffffffffu, ts, o);
+                if (lane >= o) ts += y;
+            }
+            warp_tot[lane] = ts - t;
+        }
+        __syncthreads();
+        const int excl = carry + warp_tot[warp] + x - v;
+        if (i <= n_cells) ws.cell_start[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    // rank of j inside its cell = number of earlier keypoints in the same cell (n2 is ~1e3)
+    for (int j = threadIdx.x; j < n2; j += 1024) {
+        const int c = ws.cell_of[j];
+        if (c < 0) continue;
+        int rank = 0;
+        for (int k = 0; k < j; k++) rank += (ws.cell_of[k] == c);
+        ws.items[ws.cell_start[c] + rank] = j;
+    }
+}
+
+__global__ void r2_fill_kernel(int32_t* p, size_t n, int32_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// numpy complex division (Smith's algorithm, as in numpy's loops for complex128), real part only
+__device__ __forceinline__ double cdiv_real(double ar, double ai, double br, double bi) {
+    if (fabs(br) >= fabs(bi)) {
+        if (br == 0.0 && bi == 0.0) return ar / fabs(br);
+        const double rat = bi / br, scl = 1.0 / __dadd_rn(br, __dmul_rn(bi, rat));
+        return __dmul_rn(__dadd_rn(ar, __dmul_rn(ai, rat)), scl);
+    }
+    const double rat = br / bi, scl = 1.0 / __dadd_rn(bi, __dmul_rn(br, rat));
+    return __dmul_rn(__dadd_rn(__dmul_rn(ar, rat), ai), scl);
+}
+
+// (row, col) -> H * (col, row, 1)^T, divide by w, back to (row, col)   (q9.py:62-67).  Hs holds the
+// 9 real parts followed by the 9 imaginary parts.  Products and sums are rounded one by one.
+__device__ __forceinline__ void homography_point(const double* Hs, bool cplx, double row, double col, double& tr, double& tc) {
+    const double x = col, y = row;
+    const double px = __dadd_rn(__dadd_rn(__dmul_rn(Hs[0], x), __dmul_rn(Hs[1], y)), Hs[2]);
+    const double py = __dadd_rn(__dadd_rn(__dmul_rn(Hs[3], x), __dmul_rn(Hs[4], y)), Hs[5]);
+    const double pw = __dadd_rn(__dadd_rn(__dmul_rn(Hs[6], x), __dmul_rn(Hs[7], y)), Hs[8]);
+    if (!cplx) {
+        tc = px / pw;
+        tr = py / pw;
+    } else {
+        const double ix = __dadd_rn(__dadd_rn(__dmul_rn(Hs[9], x), __dmul_rn(Hs[10], y)), Hs[11]);
+        const double iy = __dadd_rn(__dadd_rn(__dmul_rn(Hs[12], x), __dmul_rn(Hs[13], y)), Hs[14]);
+        const double iw = __dadd_rn(__dadd_rn(__dmul_rn(Hs[15], x), __dmul_rn(Hs[16], y)), Hs[17]);
+        tc = cdiv_real(px, ix, pw, iw);
+        tr = cdiv_real(py, iy, pw, iw);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+r2_points_kernel(const double* __restrict__ Hre, const double* __restrict__ Him, const double* __restrict__ kp, int n,
+                 double* __restrict__ out) {
+    __shared__ double Hs[18];
+    if (threadIdx.x < 9) {
+        Hs[threadIdx.x] = Hre[threadIdx.x];
+        Hs[9 + threadIdx.x] = Him ? Him[threadIdx.x] : 0.0;
+    }
+    __syncthreads();
+    bool cplx = false;
+#pragma unroll
+    for (int k = 0; k < 9; k++) cplx |= (Hs[9 + k] != 0.0);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double tr, tc;
+    homography_point(Hs, cplx, kp[2 * i], kp[2 * i + 1], tr, tc);
+    out[2 * i] = tr;
+    out[2 * i + 1] = tc;
+}
+
+__global__ void __launch_bounds__(RS2_THREADS)
+r2_score_kernel(const double* __restrict__ Hre, const double* __restrict__ Him, const double* __restrict__ kp1, int n1,
+                const double* __restrict__ kp2, int n2, int h, int w, Ransac2dWs ws, int32_t* __restrict__ counts_out,
+                int32_t* __restrict__ match_j_out, double* __restrict__ match_ssd_out, int32_t* __restrict__ flags_out) {
+    const int hyp = blockIdx.x;
+    __shared__ double Hs[18];
+    __shared__ int s_cnt[RS2_THREADS / 32];
+    __shared__ int s_flags;
+    if (threadIdx.x < 9) {
+        Hs[threadIdx.x] = Hre[(size_t)hyp * 9 + threadIdx.x];
+        Hs[9 + threadIdx.x] = Him ? Him[(size_t)hyp * 9 + threadIdx.x] : 0.0;
+    }
+    if (threadIdx.x == 0) s_flags = (*ws.err) ? 4 : 0;
+    __syncthreads();
+    bool cplx = false;
+#pragma unroll
+    for (int k = 0; k < 9; k++) cplx |= (Hs[9 + k] != 0.0);
+
+    int32_t* first_i = ws.first_i + (size_t)hyp * n2;
+    int32_t* jstar = ws.jstar + (size_t)hyp * n1;
+    double* ssd = ws.ssd + (size_t)hyp * n1;
+    int flags = 0;
+
+    for (int i = threadIdx.x; i < n1; i += RS2_THREADS) {
+        double tr, tc;
+        homography_point(Hs, cplx, kp1[2 * i], kp1[2 * i + 1], tr, tc);
+        int best_j = -1;
+        double best = 0.0;
+        if (isnan(tr) || isnan(tc)) flags |= 1;
+        else if (isinf(tr) || isinf(tc)) flags |= 2;
+        else {
+            const int r0 = py_int(tr), c0 = py_int(tc);
+            const int ylo = max(0, r0 - 6), yhi = min(r0 + 5, h);
+            const int xlo = max(0, c0 - 6), xhi = min(c0 + 5, w);
+            if (xhi > xlo) {
+                for (int yy = ylo; yy < yhi; yy++) {
+                    const int s = __ldg(ws.cell_start + yy * w + xlo), e = __ldg(ws.cell_start + yy * w + xhi);
+                    for (int k = s; k < e; k++) {
+                        const int j = __ldg(ws.items + k);
+                        const double dr = __dsub_rn(kp2[2 * j], tr), dc = __dsub_rn(kp2[2 * j + 1], tc);
+                        const double v = __dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dc, dc));
+                        if (best_j < 0 || v < best) { best = v; best_j = j; }   // first minimum
+                    }
+                }
+            }
+        }
+        if (best_j >= 0 && best < 10.0) {
+            atomicMin(first_i + best_j, i);
+        } else {
+            best_j = -1;
+        }
+        jstar[i] = best_j;
+        ssd[i] = best;
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n1; i += RS2_THREADS) {
+        const int j = jstar[i];
+        const bool ok = (j >= 0) && (first_i[j] == i);
+        cnt += ok;
+        if (match_j_out) match_j_out[(size_t)hyp * n1 + i] = ok ? j : -1;
+        if (match_ssd_out) match_ssd_out[(size_t)hyp * n1 + i] = ok ? ssd[i] : 0.0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if ((threadIdx.x & 31) == 0) {
+        s_cnt[threadIdx.x >> 5] = cnt;
+        if (flags) atomicOr(&s_flags, flags);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < RS2_THREADS / 32; k++) t += s_cnt[k];
+        counts_out[hyp] = t;
+        if (flags_out) flags_out[hyp] = s_flags;
+    }
+}
+
+// ---- K4B -----------------------------------------------------------------------------------------
+// One hypothesis per lane; the CTA stages a tile of correspondences in shared memory and every lane
+// streams it with broadcast reads, so a point costs two LDS per warp for 32 evaluations.  grid.y
+// splits the correspondences; per-hypothesis partial counts are combined with atomicAdd.
+constexpr int RS3_THREADS = 128;
+constexpr int RS3_TILE = 512;    // points staged per step: 512 * 48 B = 24 KB
+
+__global__ void __launch_bounds__(RS3_THREADS)
+r3_score_kernel(const double* __restrict__ T, int n_hyp, const Point4* __restrict__ P, const Point4* __restrict__ Q,
+                int n_pts, int pts_per_cta, double thresh, int32_t* __restrict__ counts) {
+    __shared__ double sp[RS3_TILE][6];
+    const int hyp = blockIdx.x * RS3_THREADS + threadIdx.x;
+    double t[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) t[k] = (hyp < n_hyp) ? T[(size_t)hyp * 16 + k] : 0.0;
+    const int p0 = blockIdx.y * pts_per_cta, p1 = min(n_pts, p0 + pts_per_cta);
+    int cnt = 0;
+    for (int base = p0; base < p1; base += RS3_TILE) {
+        const int m = min(RS3_TILE, p1 - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += RS3_THREADS) {
+            const Point4 a = load_point(P + base + k), b = load_point(Q + base + k);
+            sp[k][0] = a.x; sp[k][1] = a.y; sp[k][2] = a.z;
+            sp[k][3] = b.x; sp[k][4] = b.y; sp[k][5] = b.z;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < m; k++) {
+            const double x = sp[k][0], y = sp[k][1], z = sp[k][2];
+            const double dx = (((t[0] * x + t[1] * y) + t[2] * z) + t[3]) - sp[k][3];
+            const double dy = (((t[4] * x + t[5] * y) + t[6] * z) + t[7]) - sp[k][4];
+            const double dz = (((t[8] * x + t[9] * y) + t[10] * z) + t[11]) - sp[k][5];
+            const double r2 = dx * dx + dy * dy + dz * dz;
+            cnt += (r2 < thresh);
+        }
+    }
+    if (hyp < n_hyp && cnt) atomicAdd(counts + hyp, cnt);
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" size_t r3d_ransac2d_workspace_bytes(int n_hyp, int n1, int n2, int img_h, int img_w) {
+    if (n_hyp <= 0 || n1 <= 0 || n2 <= 0 || img_h <= 0 || img_w <= 0) return 0;
+    Ransac2dWs w;
+    Arena a(nullptr, 0);
+    ransac2d_layout(w, a, n_hyp, n1, n2, img_h, img_w);
+    return a.used + 512;
+}
+
+extern "C" int r3d_ransac2d_score(const double* H, const double* H_imag, int n_hyp, const double* kp1, int n1,
+                                  const double* kp2, int n2, int img_h, int img_w, int32_t* counts_out, int32_t* match_j_out,
+                                  double* match_ssd_out, int32_t* flags_out, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+    if (!H || !kp1 || !kp2 || !counts_out || n_hyp <= 0 || n1 <= 0 || n2 <= 0 || img_h <= 0 || img_w <= 0)
+        return R3D_ERR_INVALID;
+    if ((int64_t)img_h * img_w >= 0x7fffffffll) return R3D_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    Ransac2dWs w;
+    Arena a(workspace, workspace_bytes);
+    ransac2d_layout(w, a, n_hyp, n1, n2, img_h, img_w);
+    if (!a.ok) return R3D_ERR_WORKSPACE;
+    R3D_LAUNCH(r2_cells_kernel, (n2 + 255) / 256, 256, 0, st, kp2, n2, img_h, img_w, w);
+    R3D_LAUNCH(r2_csr_kernel, 1, 1024, 0, st, n2, img_h * img_w, w);
+    R3D_LAUNCH(r2_fill_kernel, 148, 256, 0, st, w.first_i, (size_t)n_hyp * n2, (int32_t)0x7fffffff);
+    R3D_LAUNCH(r2_score_kernel, n_hyp, RS2_THREADS, 0, st, H, H_imag, kp1, n1, kp2, n2, img_h, img_w, w, counts_out,
+               match_j_out, match_ssd_out, flags_out);
+    return R3D_OK;
+}
+
+extern "C" int r3d_ransac3d_score(const double* T, int n_hyp, const double* P, const double* Q, int n_pts, double thresh,
+                                  int32_t* counts_out, void* stream) {
+    if (!T || !P || !Q || !counts_out || n_hyp <= 0 || n_pts < 0) return R3D_ERR_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    R3D_CUDA(cudaMemsetAsync(counts_out, 0, (size_t)n_hyp * sizeof(int32_t), st));
+    if (n_pts == 0) return R3D_OK;
+    const int gx = (n_hyp + RS3_THREADS - 1) / RS3_THREADS;
+    // enough CTAs for ~4 waves of 148 SMs x 8 resident CTAs
+    int gy = (148 * 8 * 4 + gx - 1) / gx;
+    const int max_gy = (n_pts + RS3_TILE - 1) / RS3_TILE;
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    int per = (n_pts + gy - 1) / gy;
+    per = (per + RS3_TILE - 1) / RS3_TILE * RS3_TILE;
+    gy = (n_pts + per - 1) / per;
+    R3D_LAUNCH(r3_score_kernel, dim3(gx, gy), RS3_THREADS, 0, st, T, n_hyp, (const Point4*)P, (const Point4*)Q, n_pts, per,
+               thresh, counts_out);
+    return R3D_OK;
+}
+
+extern "C" int r3d_homography_points(const double* H, const double* H_imag, const double* kp, int n, double* out, void* stream) {
+    if (!H || !kp || !out || n < 0) return R3D_ERR_INVALID;
+    if (n == 0) return R3D_OK;
+    R3D_LAUNCH(r2_points_kernel, (n + 255) / 256, 256, 0, (cudaStream_t)stream, H, H_imag, kp, n, out);
+    return R3D_OK;
+}

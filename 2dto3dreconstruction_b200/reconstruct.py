@@ -1,0 +1,62 @@
+"""Drop-in for the registration-path helpers of the reference's reconstruct.py.
+
+    depth_images_to_3d_pts(depth_images, scale=1.)   reconstruct.py:336-344
+    depth_images_to_3d_pts_ld(depth_images)          reconstruct.py:347-354
+    chain_prefix(transformations)                    reconstruct.py:201-204 (prefix product only)
+
+The reference maps depth_to_voxel over the frames in a Python list comprehension; here all frames
+go through ONE K1 launch and the result is split into the same list of (N_f,3) arrays.
+"""
+import numpy as np
+
+from . import _capi as C
+from . import ops
+
+
+def _stack(depth_images):
+    frames = [np.asarray(f) for f in depth_images]
+    arr = np.stack(frames, axis=0) if not isinstance(depth_images, np.ndarray) else np.asarray(depth_images)
+    if arr.ndim == 4 and arr.shape[-1] == 1:
+        arr = arr[..., 0]
+    if arr.dtype == np.uint8:
+        arr = arr.astype(np.uint16)
+    elif arr.dtype not in (np.uint16, np.float32, np.float64):
+        if np.issubdtype(arr.dtype, np.integer) and (arr.size == 0 or (arr.min() >= 0 and arr.max() <= 65535)):
+            arr = arr.astype(np.uint16)
+        else:
+            arr = arr.astype(np.float64)
+    return np.ascontiguousarray(arr)
+
+
+def _batched(depth_images, mode, scale):
+    C.require_device()
+    arr = _stack(depth_images)
+    d = C.torch().from_numpy(arr).cuda()
+    pts, off = ops.backproject(d, mode=mode, zscale=float(scale), layout=ops.LAYOUT_XYZ)
+    off_h = off.cpu().numpy()
+    host = pts[:int(off_h[-1])].cpu().numpy()
+    return [host[off_h[f]:off_h[f + 1]] for f in range(arr.shape[0])]
+
+
+def depth_images_to_3d_pts(depth_images, scale=1.):
+    """reconstruct.py:336-344."""
+    if isinstance(scale, (int, np.integer)) and int(scale) != 1:
+        raise NotImplementedError("integer scale other than 1 is not supported by the CUDA path; pass a float")
+    out = _batched(depth_images, ops.BP_PIXEL, scale)
+    if isinstance(scale, (int, np.integer)):
+        out = [o.astype(np.int64) for o in out]
+    return out
+
+
+def depth_images_to_3d_pts_ld(depth_images):
+    """reconstruct.py:347-354."""
+    return _batched(depth_images, ops.BP_PINHOLE, 1.0)
+
+
+def chain_prefix(transformations):
+    """P_i = T_i . P_{i-1} (reconstruct.py:201-204): host side, after the pair transforms have
+    been gathered; a handful of 4x4 products."""
+    out = [np.asarray(transformations[0])]
+    for t in transformations[1:]:
+        out.append(np.dot(t, out[-1]))
+    return out

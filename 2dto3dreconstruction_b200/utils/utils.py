@@ -1,0 +1,58 @@
+"""Drop-in for the back-projection functions of the reference's utils/utils.py.
+
+    depth_to_voxel(img, scale=1)      utils/utils.py:21-45   (duplicate: utils/transformation3d.py:81-105)
+    depth_to_voxel_ld(img, scale=1)   utils/utils.py:48-76
+
+Same arguments, same return: an (N,3) array of the points with non-zero depth in row-major pixel
+order, float64 -- or int64 for depth_to_voxel with an integer scale, as NumPy's type promotion gives
+in the reference.  The arithmetic runs in the K1 kernel (csrc/backproject.cu); values are bit-exact.
+"""
+import numpy as np
+
+from .. import _capi as C
+from .. import ops
+
+
+def _device_depth(img):
+    """One frame as a CUDA [1,H,W] tensor in a dtype the kernel reads natively."""
+    C.require_device()
+    t = C.torch()
+    a = np.asarray(img)
+    if a.ndim != 2:
+        a = a.reshape(a.shape[0], a.shape[1])
+    if a.dtype == np.uint16 or a.dtype == np.float32 or a.dtype == np.float64:
+        a = np.ascontiguousarray(a)
+    elif a.dtype == np.uint8:
+        a = a.astype(np.uint16)
+    elif np.issubdtype(a.dtype, np.integer):
+        # astype(int16) keeps the low 16 bits of any integer type; uint16 holds the same bits,
+        # but x/y use the full value, so only in-range images can go through the u16 path
+        if a.size and (a.min() < 0 or a.max() > 65535):
+            raise NotImplementedError("integer depth outside [0, 65535] is not supported by the CUDA path")
+        a = a.astype(np.uint16)
+    else:
+        a = a.astype(np.float64)
+    return t.from_numpy(a[None]).cuda()
+
+
+def _run(img, scale, mode):
+    if isinstance(scale, (int, np.integer)) and not isinstance(scale, bool) and int(scale) != 1:
+        # int16 * python-int stays int16 in NumPy and can wrap; not reproduced on the device
+        raise NotImplementedError("integer scale other than 1 is not supported by the CUDA path; pass a float")
+    d = _device_depth(img)
+    pts, off = ops.backproject(d, mode=mode, zscale=float(scale), layout=ops.LAYOUT_XYZ)
+    n = int(off[1].item())
+    return pts[:n].cpu().numpy()
+
+
+def depth_to_voxel(img, scale=1):
+    """Pixel-space cloud (u, v, int16(depth) * scale), zero rows dropped (utils/utils.py:21-45)."""
+    out = _run(img, scale, ops.BP_PIXEL)
+    if isinstance(scale, (int, np.integer)):
+        return out.astype(np.int64)     # the reference stacks int64 pixel grids with an int16 depth
+    return out
+
+
+def depth_to_voxel_ld(img, scale=1):
+    """Pinhole cloud with the reference's fixed intrinsics (utils/utils.py:48-76)."""
+    return _run(img, scale, ops.BP_PINHOLE)

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the registration hot path (BASELINE.json: ICP frame-pairs/s and correspondences/s
+on synthetic 640x480 depth pairs; configs[2]: batch of 1024 pairs, back-projection + 30-iteration
+ICP, sharded over 1/2/4/8 GPUs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" registers every pair of the rank's batch once: K1 back-projection of both frames, grid
+build, 30 ICP iterations (tolerance 0, partial_set_size 1.0), one all-gather of the 4x4s when N > 1.
+Weak scaling: every GPU holds `--pairs` (default 1024) pairs; `value` counts all ranks' pairs.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+H, W = 480, 640
+ICP_ITERS = 30
+ALGO_BYTES_PER_CORR = 40.0     # 16 src + 16 dst (amortised) + 8 idx/dist
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("R3D_BENCH_PAIRS", "1024")), help="pairs per GPU")
+    ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "8")))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "2")))
+    ap.add_argument("--partial", type=float, default=1.0)
+    ap.add_argument("--cpu-sample-iters", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def synth_batch_torch(n_pairs, seed, device):
+    """The SURVEY.md section 8d surface model, generated on the device (NumPy would need ~20 s for
+    1024 pairs): frame a = surface + N(0,2), 10% dropout; frame b = surface shifted by integer
+    (du,dv) in [-8,8]^2 and dz in [-20,20], fresh noise and dropout.  uint16 [n,480,640] x 2."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + seed)
+    u = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
+    v = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
+    a = torch.empty((n_pairs, H, W), dtype=torch.uint16, device=device)
+    b = torch.empty((n_pairs, H, W), dtype=torch.uint16, device=device)
+    step = 64
+    for s in range(0, n_pairs, step):
+        e = min(n_pairs, s + step)
+        k = e - s
+        du = torch.randint(-8, 9, (k, 1, 1), generator=g, device=device).float()
+        dv = torch.randint(-8, 9, (k, 1, 1), generator=g, device=device).float()
+        dz = torch.randint(-20, 21, (k, 1, 1), generator=g, device=device).float()
+        fa = 2000.0 + 600.0 * torch.sin(u / 97.0) + 400.0 * torch.cos(v / 61.0) + torch.randn((k, H, W), generator=g, device=device) * 2.0
+        fb = (2000.0 + 600.0 * torch.sin((u + du) / 97.0) + 400.0 * torch.cos((v + dv) / 61.0) + dz
+              + torch.randn((k, H, W), generator=g, device=device) * 2.0)
+        fa = torch.round(fa)
+        fb = torch.round(fb)
+        fa[torch.rand((k, H, W), generator=g, device=device) < 0.10] = 0
+        fb[torch.rand((k, H, W), generator=g, device=device) < 0.10] = 0
+        a[s:e] = fa.to(torch.int32).to(torch.uint16)
+        b[s:e] = fb.to(torch.int32).to(torch.uint16)
+    return a, b
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu), "-f", self.path], stdout=subprocess.DEVNULL,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+            sm = sorted(float(r[1]) for r in rows if len(r) >= 9)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["samples"] = len(sm)
+                out["power_w_max"] = max(float(r[3]) for r in rows if len(r) >= 9)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for k, nm in enumerate(names):
+                    if any("Active" == r[5 + k].strip() for r in rows if len(r) >= 9):
+                        out["reasons"].append(nm)
+        except Exception:
+            pass
+        return out
+
+
+def run_reference(args):
+    """The reference's own CPU path (oracle port: NumPy + scikit-learn KD-tree, as utils/icp.py
+    calls them) on all host cores, same metric and config.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    from oracle import cpu_bench
+    from oracle import ref_port as O
+    cores = os.cpu_count() or 1
+    n = min(cores, 64)
+    frames = [O.synth_depth_pair(k) for k in range(n)]
+    fa = np.stack([f[0] for f in frames])
+    fb = np.stack([f[1] for f in frames])
+    vals, corr = [], []
+    for s in range(args.warmup + args.steps):
+        r = cpu_bench.time_pairs(fa, fb, sample_iters=args.cpu_sample_iters, full_iters=ICP_ITERS, partial=args.partial,
+                                 cores=n)
+        if s >= args.warmup:
+            vals.append(r["pairs_per_s"])
+            corr.append(r["corr_per_s"])
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "icp_frame_pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * n / v, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "correspondences_per_sec": sum(corr) / len(corr),
+        "config": {"workload": "synthetic 640x480 depth pairs: pinhole back-projection + %d-iteration ICP (tolerance 0, "
+                               "partial_set_size %.2f)" % (ICP_ITERS, args.partial), "pairs_per_step": n,
+                   "icp_iterations": ICP_ITERS},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import importlib
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    pkg = importlib.import_module("2dto3dreconstruction_b200")
+    pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
+    C = pkg._capi
+    C.require_device()
+    L = C.lib()
+
+    P = args.pairs
+    depth_a, depth_b = synth_batch_torch(P, seed=rank, device=dev)
+    torch.cuda.synchronize()
+    kw = dict(max_iterations=ICP_ITERS, tolerance=0.0, partial_set_size=args.partial,
+              pairs_per_chunk=args.pairs_per_chunk, n_streams=args.streams)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        out = pipeline.register_depth_pairs(depth_a, depth_b, **kw)
+        if world > 1:
+            out["T_all"] = pipeline.gather_transforms(out["T"], P * world)
+        return out
+
+    # ---------------- device-resident timing (`value`) ----------------
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = C.launch_count()
+    L.r3d_nn_timing_enable(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    L.r3d_nn_timing_enable(0)
+    ms_total = e0.elapsed_time(e1)
+    launches = C.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    import ctypes
+    nn_ms, nn_launches, nn_q = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    C.check(L.r3d_nn_timing_read(ctypes.byref(nn_ms), ctypes.byref(nn_launches), ctypes.byref(nn_q), 1))
+
+    n_src = out["n_src"].cpu().numpy().astype(np.int64)
+    iters = out["iters"].cpu().numpy().astype(np.int64)
+    executed = np.minimum(iters, ICP_ITERS)               # iterations actually run per pair
+    corr_per_step = int((n_src * executed).sum())
+
+    # ---------------- end-to-end timing (`e2e`): host buffers in, host results out ----------------
+    host_a = torch.empty((P, H, W), dtype=torch.uint16, pin_memory=True)
+    host_b = torch.empty((P, H, W), dtype=torch.uint16, pin_memory=True)
+    host_a.copy_(depth_a)
+    host_b.copy_(depth_b)
+    torch.cuda.synchronize()
+
+    def step_host():
+        r = pipeline.register_depth_pairs(host_a, host_b, **kw)       # synchronous: results are on the host
+        if world > 1:
+            r["T_all"] = pipeline.gather_transforms(torch.from_numpy(r["T"]).to(dev), P * world)
+        return r
+
+    for _ in range(2):
+        rh = step_host()
+    barrier()
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(args.steps):
+        rh = step_host()
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1)
+    e2e_wall_ms = (time.perf_counter() - t0) * 1000.0
+    parity_dev_host = bool(np.array_equal(rh["T"], out["T"].cpu().numpy()))
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(tt[0]), float(tt[1])
+        cc = torch.tensor([corr_per_step, launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        corr_total, launches_total = int(cc[0]), int(cc[1])
+    else:
+        corr_total, launches_total = corr_per_step, launches
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    pairs_total = P * world
+    value = pairs_total / (ms_per_step / 1000.0)
+    e2e_value = pairs_total / (e2e_ms / args.steps / 1000.0)
+    peak, peak_src = peak_hbm()
+    nn_avg_ms = nn_ms.value / max(nn_launches.value, 1)
+    # rank 0's nn launches processed rank 0's correspondences
+    achieved = ALGO_BYTES_PER_CORR * corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "nn_kernel (K2 exact grid NN + fused K3 moments)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_correspondence": ALGO_BYTES_PER_CORR, "launches_timed": int(nn_launches.value),
+        "avg_launch_ms": nn_avg_ms, "kernel_share_of_step": nn_ms.value / ms_total,
+        "correspondences_per_sec_in_kernel": corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12),
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        cores = os.cpu_count() or 1
+        n = min(cores, P, 64)
+        fa = depth_a[:n].cpu().numpy()
+        fb = depth_b[:n].cpu().numpy()
+        r = cpu_bench.time_pairs(fa, fb, sample_iters=args.cpu_sample_iters, full_iters=ICP_ITERS, partial=args.partial, cores=n)
+        cpu_baseline = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                        "sample": r["sample"], "correspondences_per_sec": r["corr_per_s"], "wall_s": r["wall_s"]}
+
+    line = {
+        "metric": "icp_frame_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "correspondences_per_sec": corr_total / (ms_per_step / 1000.0),
+        "config": {"workload": "synthetic 640x480 depth-pair batch: pinhole back-projection + %d-iteration ICP (tolerance 0, "
+                               "partial_set_size %.2f), BASELINE.json configs[2]" % (ICP_ITERS, args.partial),
+                   "pairs_per_gpu": P, "global_pairs": pairs_total, "icp_iterations": ICP_ITERS, "pairs_per_chunk": args.pairs_per_chunk,
+                   "streams": args.streams, "parallelism": "pairs sharded x%d, one all-gather of 4x4s" % world,
+                   "l2": "inputs %.2f GB per step per GPU (> 126 MB L2); no flush needed" % (2 * P * H * W * 2 / 1e9)},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * H * W * 2) * world,
+                "d2h_bytes_per_step": int(P * (128 + 4 + 8 + 4 + 4)) * world, "ms_per_step": e2e_ms / args.steps,
+                "wall_ms_per_step_rank0": e2e_wall_ms / args.steps,
+                "api": "pipeline.register_depth_pairs(host uint16 frames) -> r3d_register_depth_pairs_host",
+                "device_vs_host_results_identical": parity_dev_host},
+        "gpu_launches": launches_total,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,72 @@
+"""K1 parity: CUDA back-projection vs the reference's outputs (golden) and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, sub
+from oracle import ref_port as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_bit_exact():
+    U = sub("utils.utils")
+    g = load_golden("backproject")
+    small = g["small"]
+    for got, key in [
+        (U.depth_to_voxel_ld(small), "small_ld"),
+        (U.depth_to_voxel_ld(small, 0.5), "small_ld_half"),
+        (U.depth_to_voxel(small), "small_px"),
+        (U.depth_to_voxel(small, 0.1), "small_px_tenth"),
+        (U.depth_to_voxel(small, 1.), "small_px_t3d"),
+        (U.depth_to_voxel(g["fimg"]), "fimg_px"),
+        (U.depth_to_voxel(g["fimg"], 2.5), "fimg_px_scaled"),
+        (U.depth_to_voxel_ld(g["crop"]), "crop_ld"),
+    ]:
+        want = g[key]
+        assert got.dtype == want.dtype, key
+        assert got.shape == want.shape, key
+        assert np.array_equal(got, want), key
+
+
+def test_full_frame_vs_oracle_and_batch():
+    R = sub("reconstruct")
+    frames = np.stack([O.synth_depth_pair(k)[0] for k in range(3)] + [O.synth_depth_pair(0)[1]])
+    frames[1, :, :] = 0                      # an all-empty frame
+    frames[2, 100:200, :] = 40000            # int16 wrap: negative z, kept
+    got = R.depth_images_to_3d_pts_ld(frames)
+    want = O.depth_images_to_3d_pts_ld(frames)
+    assert len(got) == len(want) == 4
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and a.dtype == b.dtype
+        assert np.array_equal(a, b)
+    assert got[1].shape == (0, 3)
+    got = R.depth_images_to_3d_pts(frames, scale=0.1)
+    want = O.depth_images_to_3d_pts(frames, scale=0.1)
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    got = R.depth_images_to_3d_pts(list(frames))      # scale defaults to 1. (float)
+    want = O.depth_images_to_3d_pts(list(frames))
+    for a, b in zip(got, want):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def test_ragged_sizes_and_layouts():
+    import torch
+    ops = sub("ops")
+    rng = np.random.default_rng(5)
+    for (h, w) in [(1, 1), (3, 7), (33, 61), (480, 640), (31, 2049)]:
+        img = rng.integers(0, 5000, size=(2, h, w)).astype(np.uint16)
+        img[rng.random(img.shape) < 0.3] = 0
+        d = torch.from_numpy(img).cuda()
+        pts, off = ops.backproject(d, layout=ops.LAYOUT_XYZW)
+        off = off.cpu().numpy()
+        for f in range(2):
+            want = O.depth_to_voxel_ld(img[f])
+            got = pts[off[f]:off[f + 1]].cpu().numpy()
+            assert np.array_equal(got[:, :3], want)
+            # w lane carries the point's index inside its frame
+            assert np.array_equal(got[:, 3].view(np.int64) & 0xffffffff, np.arange(len(want)))
+        p32, off32 = ops.backproject(d, layout=ops.LAYOUT_XYZW_F32)
+        got32 = p32[:int(off32[-1])].cpu().numpy()
+        want32 = np.concatenate([O.depth_to_voxel_ld(img[f]) for f in range(2)]).astype(np.float32)
+        assert np.array_equal(got32[:, :3], want32)

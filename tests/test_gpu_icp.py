@@ -1,0 +1,117 @@
+"""ICP parity: the device loop vs utils/icp.py (golden from the reference, and the oracle)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, sub
+from oracle import ref_port as O
+from parity import assert_transform_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("full30", dict(max_iterations=30, tolerance=0.0, partial_set_size=1.0)),
+    ("part30", dict(max_iterations=30, tolerance=0.0, partial_set_size=0.7)),
+    ("tol", dict(max_iterations=50, tolerance=0.001, partial_set_size=0.7)),
+    ("default", dict()),
+])
+def test_golden(tag, kw):
+    icp = sub("utils.icp")
+    g = load_golden("icp")
+    A, B = g["cloud_a"], g["cloud_b"]
+    T, dist, it = icp.icp(A, B, **kw)
+    assert it == int(g[tag + "_iters"])
+    assert_transform_parity(T, g[tag + "_T"], O.scene_extent(B), tag, 1e-7, 1e-8)
+    assert dist.shape == g[tag + "_dist_sorted"].shape
+    np.testing.assert_allclose(np.sort(dist), g[tag + "_dist_sorted"], rtol=1e-7, atol=1e-7)
+
+
+def test_golden_init_pose():
+    icp = sub("utils.icp")
+    g = load_golden("icp")
+    for tag, n in [("init", 10), ("aff", 6)]:
+        T, dist, it = icp.icp(g["cloud_a"], g["cloud_b"], init_pose=g["init" if tag == "init" else "init_aff"],
+                              max_iterations=n, tolerance=0.0)
+        assert it == int(g[tag + "_iters"])
+        assert_transform_parity(T, g[tag + "_T"], O.scene_extent(g["cloud_b"]), tag, 1e-7, 1e-8)
+
+
+def test_stepwise_vs_oracle_trace():
+    """Every iteration's correspondences (indices) must match the oracle run with brute-force NN."""
+    ops = sub("ops")
+    C = sub("_capi")
+    g = load_golden("icp")
+    A, B = g["cloud_a"], g["cloud_b"]
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    so, do = ops._offsets([len(A)]), ops._offsets([len(B)])
+    trace = []
+    O.icp(A, B, max_iterations=6, tolerance=0.0, partial_set_size=0.8, nn=O.nearest_neighbor_brute, trace=trace)
+    for k in range(1, 7):
+        r = ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=k, tolerance=0.0, partial_set_size=0.8,
+                          want_last=True)
+        keep = r["keep"].cpu().numpy().astype(bool)
+        idx = r["idx"].cpu().numpy()
+        kept_ref, idx_ref, dist_ref, _ = trace[k - 1]
+        assert keep.sum() == len(kept_ref)
+        assert np.array_equal(np.nonzero(keep)[0], np.sort(kept_ref)), "kept set, iteration %d" % k
+        order = np.argsort(kept_ref)
+        assert np.array_equal(idx[keep], idx_ref[order]), "indices, iteration %d" % k
+        np.testing.assert_allclose(r["dist"].cpu().numpy()[keep], dist_ref[order], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("partial", [1.0, 0.7])
+def test_full_density_pair(partial):
+    """One full 640x480 synthetic pair, 5 iterations, vs the oracle with the reference's KD-tree."""
+    icp = sub("utils.icp")
+    a, b = O.synth_depth_pair(3)
+    A, B = O.depth_to_voxel_ld(a), O.depth_to_voxel_ld(b)
+    T, dist, it = icp.icp(A, B, max_iterations=5, tolerance=0.0, partial_set_size=partial)
+    Tr, dr, itr = O.icp(A, B, max_iterations=5, tolerance=0.0, partial_set_size=partial)
+    assert it == itr == 6
+    assert_transform_parity(T, Tr, O.scene_extent(B), "full pair")
+    np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=1e-6, atol=1e-6)
+
+
+def test_batch_matches_single_and_is_deterministic():
+    ops = sub("ops")
+    C = sub("_capi")
+    icp = sub("utils.icp")
+    clouds = []
+    for k in range(4):
+        a, b = O.synth_depth_pair(10 + k, h=48, w=64)
+        fa = np.zeros((480, 640), np.uint16)
+        fb = np.zeros((480, 640), np.uint16)
+        fa[200:248, 280:344] = a
+        fb[200:248, 280:344] = b
+        clouds.append((O.depth_to_voxel_ld(fa), O.depth_to_voxel_ld(fb)))
+    ns = [len(c[0]) for c in clouds]
+    ms = [len(c[1]) for c in clouds]
+    s = ops.pack_xyzw(C.to_device(np.concatenate([c[0] for c in clouds])))
+    d = ops.pack_xyzw(C.to_device(np.concatenate([c[1] for c in clouds])))
+    r1 = ops.icp_batch(s, ops._offsets(ns), d, ops._offsets(ms), 4, max(ns), max(ms), max_iterations=15, tolerance=1e-4,
+                       partial_set_size=0.9)
+    r2 = ops.icp_batch(s, ops._offsets(ns), d, ops._offsets(ms), 4, max(ns), max(ms), max_iterations=15, tolerance=1e-4,
+                       partial_set_size=0.9)
+    assert np.array_equal(r1["T"].cpu().numpy(), r2["T"].cpu().numpy()), "bitwise reproducible"
+    for p in range(4):
+        T, _, it = icp.icp(clouds[p][0], clouds[p][1], max_iterations=15, tolerance=1e-4, partial_set_size=0.9)
+        assert np.array_equal(T, r1["T"][p].cpu().numpy())
+        assert it == int(r1["iters"][p])
+        Tr, _, itr = O.icp(clouds[p][0], clouds[p][1], max_iterations=15, tolerance=1e-4, partial_set_size=0.9)
+        assert it == itr
+        assert_transform_parity(T, Tr, O.scene_extent(clouds[p][1]), "pair %d" % p, 1e-7, 1e-8)
+
+
+def test_zero_iterations_and_identity():
+    icp = sub("utils.icp")
+    rng = np.random.default_rng(0)
+    A = rng.normal(size=(500, 3)) * 10
+    T, dist, it = icp.icp(A, A.copy(), max_iterations=0)
+    assert dist is None and it == 1
+    np.testing.assert_allclose(T, np.eye(4), atol=1e-12)
+    T, dist, it = icp.icp(A, A.copy(), max_iterations=5, tolerance=1e-9)
+    Tr, dr, itr = O.icp(A, A.copy(), max_iterations=5, tolerance=1e-9)
+    assert it == itr
+    np.testing.assert_allclose(T, np.eye(4), atol=1e-12)
+    assert np.all(dist == 0)

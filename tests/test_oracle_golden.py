@@ -1,0 +1,151 @@
+"""The oracle (oracle/ref_port.py) against vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import ref_port as O
+
+
+def test_backproject_bit_exact():
+    g = load_golden("backproject")
+    small = g["small"]
+    for got, key in [
+        (O.depth_to_voxel_ld(small), "small_ld"),
+        (O.depth_to_voxel_ld(small, 0.5), "small_ld_half"),
+        (O.depth_to_voxel(small), "small_px"),
+        (O.depth_to_voxel(small, 0.1), "small_px_tenth"),
+        (O.depth_to_voxel(small, 1.), "small_px_t3d"),
+        (O.depth_to_voxel(g["fimg"]), "fimg_px"),
+        (O.depth_to_voxel(g["fimg"], 2.5), "fimg_px_scaled"),
+        (O.depth_to_voxel_ld(g["crop"]), "crop_ld"),
+    ]:
+        want = g[key]
+        assert got.dtype == want.dtype, key
+        assert got.shape == want.shape, key
+        assert np.array_equal(got, want), key
+    # int16 wrap-around rows are kept with negative z
+    assert (O.depth_to_voxel_ld(small)[:, 2] < 0).sum() == 3
+
+
+def test_nearest_neighbor_kdtree_and_brute():
+    g = load_golden("nearest_neighbor")
+    d, i = O.nearest_neighbor(g["src"], g["dst"])
+    assert np.array_equal(i, g["idx"]) and np.array_equal(d, g["dist"])
+    db, ib = O.nearest_neighbor_brute(g["src"], g["dst"])
+    assert np.array_equal(ib, g["idx"])
+    np.testing.assert_allclose(db, g["dist"], rtol=1e-14)
+    # lattice data: indices may differ on exact ties, distances may not
+    dl, il = O.nearest_neighbor_brute(g["lat_src"], g["lat_dst"])
+    np.testing.assert_allclose(dl, g["lat_dist"], rtol=1e-14, atol=0)
+    tie = il != g["lat_idx"]
+    assert tie.sum() > 0, "fixture is meant to contain exact ties"
+    d_ref_choice = np.linalg.norm(g["lat_src"][tie] - g["lat_dst"][g["lat_idx"][tie]], axis=1)
+    np.testing.assert_allclose(d_ref_choice, dl[tie], rtol=1e-14)
+    assert (il[tie] < g["lat_idx"][tie]).all(), "brute force breaks ties towards the lowest index"
+
+
+def test_kabsch():
+    g = load_golden("kabsch")
+    assert np.allclose(O.best_fit_transform(g["A"], g["B"]), g["T"], rtol=0, atol=1e-12)
+    assert np.allclose(O.best_fit_transform(g["A"], g["B_reflect"]), g["T_reflect"], rtol=0, atol=1e-12)
+    for a, b, rk, tk in [("A", "B", "R1", "t1"), ("A", "B_reflect", "R2", "t2"), ("Ai", "Bi", "R3", "t3")]:
+        R, t = O.rigid_transform_3D(g[a].T, g[b].T)
+        assert t.shape == (3, 1)
+        assert np.allclose(R, g[rk], atol=1e-12) and np.allclose(t, g[tk], atol=1e-9)
+    with pytest.raises(Exception):
+        O.rigid_transform_3D(g["A"], g["B"])          # (K,3): not 3xN
+    with pytest.raises(AssertionError):
+        O.rigid_transform_3D(g["A"].T, g["B"][:2].T[:2])
+
+
+@pytest.mark.parametrize("tag,kw", [
+    ("full30", dict(max_iterations=30, tolerance=0.0, partial_set_size=1.0)),
+    ("part30", dict(max_iterations=30, tolerance=0.0, partial_set_size=0.7)),
+    ("tol", dict(max_iterations=50, tolerance=0.001, partial_set_size=0.7)),
+    ("default", dict()),
+])
+def test_icp(tag, kw):
+    g = load_golden("icp")
+    ca, cb = O.depth_to_voxel_ld(_embed(g["frame_a"])), O.depth_to_voxel_ld(_embed(g["frame_b"]))
+    assert np.array_equal(ca, g["cloud_a"]) and np.array_equal(cb, g["cloud_b"])
+    T, dist, it = O.icp(ca, cb, **kw)
+    assert it == int(g[tag + "_iters"])
+    np.testing.assert_allclose(T, g[tag + "_T"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(np.sort(dist), g[tag + "_dist_sorted"], rtol=1e-10, atol=1e-10)
+
+
+def test_icp_init_pose():
+    g = load_golden("icp")
+    for tag, init, n in [("init", g["init"], 10), ("aff", g["init_aff"], 6)]:
+        T, dist, it = O.icp(g["cloud_a"], g["cloud_b"], init_pose=init, max_iterations=n, tolerance=0.0)
+        assert it == int(g[tag + "_iters"])
+        np.testing.assert_allclose(T, g[tag + "_T"], rtol=0, atol=1e-10)
+
+
+def _embed(small):
+    f = np.zeros((480, 640), np.uint16)
+    f[200:260, 280:360] = small
+    return f
+
+
+def test_synth_pair_is_deterministic():
+    g = load_golden("icp")
+    a, b = O.synth_depth_pair(0, h=60, w=80)
+    assert np.array_equal(a, g["frame_a"]) and np.array_equal(b, g["frame_b"])
+
+
+def test_affine_fit():
+    g = load_golden("affine")
+    h = O.homo_rigid_transform_3d(g["p"], g["q"])
+    np.testing.assert_allclose(h, g["h"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(O.homo_rigid_transform_3d_scipy(g["p"], g["q"]), g["h"], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(O.get_transformed_points(g["cloud"], g["h"]), g["cloud_h"])
+
+
+def test_ransac2d_pieces():
+    g = load_golden("ransac2d")
+    Hh, Ww = g["img_shape"]
+    orig = g["xy1"][:, ::-1]
+    prime = g["xy2"][:, ::-1]
+    binned = O.make_binned_array((Hh, Ww), prime)
+    # CSR form must list the same (cell, item) pairs in the same order as the reference's
+    # list-of-lists walked row-major
+    cells = np.repeat(np.arange(Hh * Ww), np.diff(binned["start"]))
+    assert np.array_equal(cells, g["binned_cells"]) and np.array_equal(binned["items"], g["binned_items"])
+    assert (g["binned_cells"] // Ww == Hh - 1).any(), "fixture exercises the negative-index wrap"
+    for k in range(3):
+        tp = O.q9_get_transformed_points(orig, g["Hs"][k])
+        assert np.array_equal(tp, g["tp%d" % k])
+        m, s = O.get_ssd_v2(orig, tp, prime, binned)
+        assert np.array_equal(m, g["m%d" % k])
+        assert np.array_equal(s, g["s%d" % k])
+    assert len(g["m0"]) > 100
+
+
+def test_ransac2d_loop_seeded():
+    g = load_golden("ransac2d")
+    np.random.seed(7)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Hs, picks = O.ransac_hypotheses(g["xy1"], g["xy2"], g["bf"])
+    assert np.array_equal(picks, g["picks"])
+    assert np.array_equal(Hs, g["dlt_H"])
+    np.random.seed(7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        H, fm, counts = O.ransac_loop_pts(tuple(g["img_shape"]), g["xy1"], g["xy2"], g["bf"])
+    assert np.array_equal(fm, g["final_matches"])
+    np.testing.assert_allclose(H, g["H_final"], rtol=1e-9, atol=1e-12)
+    assert counts.max() > 100
+
+
+def test_chain_prefix():
+    rng = np.random.default_rng(0)
+    Ts = [np.eye(4) + rng.normal(size=(4, 4)) * 0.01 for _ in range(5)]
+    P = O.chain_prefix(Ts)
+    assert np.allclose(P[3], Ts[3] @ Ts[2] @ Ts[1] @ Ts[0])
