@@ -60,6 +60,7 @@ SIGNATURES = {
     "r3d_register_depth_pairs_host": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_double,
                                               c_double, ctypes.POINTER(IcpParams), c_int, c_int, c_void_p, c_void_p,
                                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "r3d_set_option": (c_int, [c_int, c_double]),
     "r3d_launch_count": (ctypes.c_uint64, []),
     "r3d_nn_timing_enable": (None, [c_int]),
     "r3d_nn_timing_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int]),

@@ -54,7 +54,7 @@ __device__ inline int bits_for(unsigned long long count) {   // bits needed to i
 }
 
 __global__ void plan_kernel(const unsigned long long* __restrict__ bbox, const int32_t* __restrict__ dst_off,
-                            double cell_size, int n_pairs, GridParams* __restrict__ params) {
+                            double cell_size, int n_pairs, GridParams* __restrict__ params, SortDesc* __restrict__ desc) {
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= n_pairs) return;
     GridParams g;
@@ -98,6 +98,8 @@ __global__ void plan_kernel(const unsigned long long* __restrict__ bbox, const i
     g.pad = 0;
     for (int k = 0; k < 3; k++) g.shift[k] = 0.5 * (mn[k] + mx[k]);
     params[pair] = g;
+    desc[pair].n = g.n_pts;
+    desc[pair].n_passes = g.n_passes;
 }
 
 // ---- keys -----------------------------------------------------------------------------------
@@ -124,11 +126,11 @@ keys_kernel(const Point4* __restrict__ dst, const int32_t* __restrict__ dst_off,
 // Pass k reads buffer (k & 1) and writes buffer ((k + 1) & 1).  Passes beyond a pair's
 // n_passes do nothing for that pair, so its result stays in buffer (n_passes & 1).
 __global__ void __launch_bounds__(GB_THREADS)
-rs_hist(const uint32_t* __restrict__ keys, const GridParams* __restrict__ params, uint32_t* __restrict__ hist, int pass,
+rs_hist(const uint32_t* __restrict__ keys, const SortDesc* __restrict__ desc, uint32_t* __restrict__ hist, int pass,
         int max_dst, int tiles) {
     const int pair = blockIdx.y, tile = blockIdx.x;
-    const int n = params[pair].n_pts;
-    if (pass >= params[pair].n_passes) return;
+    const int n = desc[pair].n;
+    if (pass >= desc[pair].n_passes || tile * RS_TILE >= n) return;
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -140,15 +142,19 @@ rs_hist(const uint32_t* __restrict__ keys, const GridParams* __restrict__ params
         if (i < n) atomicAdd(&h[(k[i] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    hist[((size_t)pair * 256 + threadIdx.x) * tiles + tile] = h[threadIdx.x];
+    const int my_tiles = (n + RS_TILE - 1) / RS_TILE;
+    hist[(size_t)pair * 256 * tiles + (size_t)threadIdx.x * my_tiles + tile] = h[threadIdx.x];
 }
 
 // exclusive scan over a pair's [256][tiles] histogram (digit-major), one CTA per pair
 __global__ void __launch_bounds__(1024)
-rs_scan(uint32_t* __restrict__ hist, const GridParams* __restrict__ params, int pass, int tiles) {
+rs_scan(uint32_t* __restrict__ hist, const SortDesc* __restrict__ desc, int pass, int tiles_cap) {
     const int pair = blockIdx.x;
-    if (pass >= params[pair].n_passes) return;
-    uint32_t* h = hist + (size_t)pair * 256 * tiles;
+    if (pass >= desc[pair].n_passes) return;
+    // only the tiles this pair really has take part: the histogram is [256][tiles] with the pair's
+    // own tile count as row length, so the scan length follows the cloud size, not the capacity
+    const int tiles = (desc[pair].n + RS_TILE - 1) / RS_TILE;
+    uint32_t* h = hist + (size_t)pair * 256 * tiles_cap;
     const int n = 256 * tiles;
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry;
@@ -186,11 +192,11 @@ rs_scan(uint32_t* __restrict__ hist, const GridParams* __restrict__ params, int 
 
 __global__ void __launch_bounds__(GB_THREADS)
 rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
-           uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ offsets, const GridParams* __restrict__ params,
+           uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ offsets, const SortDesc* __restrict__ desc,
            int pass, int max_dst, int tiles) {
     const int pair = blockIdx.y, tile = blockIdx.x;
-    const int n = params[pair].n_pts;
-    if (pass >= params[pair].n_passes) return;
+    const int n = desc[pair].n;
+    if (pass >= desc[pair].n_passes || tile * RS_TILE >= n) return;
     constexpr int NW = GB_THREADS / 32;
     __shared__ uint32_t wcnt[NW][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,7 +229,8 @@ rs_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ va
     __syncthreads();
     {   // digit = threadIdx.x: running base over warps, seeded with the global offset
         const uint32_t d = threadIdx.x;
-        uint32_t run = offsets[((size_t)pair * 256 + d) * tiles + tile];
+        const int my_tiles = (n + RS_TILE - 1) / RS_TILE;
+        uint32_t run = offsets[(size_t)pair * 256 * tiles + (size_t)d * my_tiles + tile];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
             const uint32_t c = wcnt[w][d];
@@ -401,29 +408,47 @@ cell_table_kernel(GridWorkspace w) {
     const int pair = blockIdx.y;
     const GridParams* gp = w.params + pair;
     const int n_blocks = gp->n_blocks;
-    const int b = blockIdx.x * (GB_THREADS / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     uint32_t* cs = w.cell_start + (size_t)pair * ((size_t)64 * w.max_dst + 64);
-    if (b == 0 && lane == 0) cs[(size_t)64 * n_blocks] = (uint32_t)gp->n_pts;   // global sentinel
-    if (b >= n_blocks) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cs[(size_t)64 * n_blocks] = (uint32_t)gp->n_pts;   // global sentinel
     const uint32_t* keys = w.keys[gp->n_passes & 1] + (size_t)pair * w.max_dst;
     const uint32_t* bf = w.block_first + (size_t)pair * (w.max_dst + 1);
-    const uint32_t first = bf[b], last = bf[b + 1];
-    const uint32_t blk = w.block_key[(size_t)pair * w.max_dst + b];
+    const int warps = gridDim.x * (GB_THREADS / 32);
+    for (int b = blockIdx.x * (GB_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+        const uint32_t first = bf[b], last = bf[b + 1];
+        const uint32_t blk = w.block_key[(size_t)pair * w.max_dst + b];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint32_t f = (uint32_t)(lane + 32 * h);
-        const uint32_t target = (blk << 6) | f;
-        uint32_t lo = first, hi = last;          // first position with key >= target
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (keys[mid] < target) lo = mid + 1; else hi = mid;
+        for (int h = 0; h < 2; h++) {
+            const uint32_t f = (uint32_t)(lane + 32 * h);
+            const uint32_t target = (blk << 6) | f;
+            uint32_t lo = first, hi = last;          // first position with key >= target
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (keys[mid] < target) lo = mid + 1; else hi = mid;
+            }
+            cs[(size_t)64 * b + f] = lo;
         }
-        cs[(size_t)64 * b + f] = lo;
     }
 }
 
 // ---- host ---------------------------------------------------------------------------------------
+// Batched stable LSD radix sort of 32-bit keys with 32-bit payloads: 4 passes of 8 bits; pass k reads
+// buffer (k & 1) and writes the other one; a pair whose keys need fewer bits skips the top passes,
+// so its result is in buffer (desc.n_passes & 1).
+int radix_sort_pairs(uint32_t* const keys[2], uint32_t* const vals[2], uint32_t* hist, const SortDesc* desc, int n_pairs,
+                     int cap, int tiles, cudaStream_t st) {
+    for (int pass = 0; pass < 4; pass++) {
+        const int in = pass & 1, out = in ^ 1;
+        R3D_LAUNCH(rs_hist, dim3(tiles, n_pairs), GB_THREADS, 0, st, keys[in], desc, hist, pass, cap, tiles);
+        R3D_LAUNCH(rs_scan, n_pairs, 1024, 0, st, hist, desc, pass, tiles);
+        R3D_LAUNCH(rs_scatter, dim3(tiles, n_pairs), GB_THREADS, 0, st, keys[in], vals[in], keys[out], vals[out], hist, desc,
+                   pass, cap, tiles);
+    }
+    return R3D_OK;
+}
+
+int radix_tiles(int cap) { return (cap + RS_TILE - 1) / RS_TILE; }
+
 size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_dst) {
     w.n_pairs = n_pairs;
     w.max_dst = max_dst;
@@ -434,6 +459,7 @@ size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_ds
     const size_t P = (size_t)n_pairs, M = (size_t)max_dst;
     w.bbox = a.take<unsigned long long>(P * 6);
     w.params = a.take<GridParams>(P);
+    w.sort_desc = a.take<SortDesc>(P);
     w.keys[0] = a.take<uint32_t>(P * M);
     w.keys[1] = a.take<uint32_t>(P * M);
     w.vals[0] = a.take<uint32_t>(P * M);
@@ -456,24 +482,14 @@ int grid_build(const GridWorkspace& w, const Point4* dst, const int32_t* dst_off
         int bx = pt_blocks < 64 ? pt_blocks : 64;
         R3D_LAUNCH(bbox_kernel, dim3(bx, P), GB_THREADS, 0, st, dst, dst_off, w.bbox);
     }
-    R3D_LAUNCH(plan_kernel, (P + 127) / 128, 128, 0, st, w.bbox, dst_off, cell_size, P, w.params);
+    R3D_LAUNCH(plan_kernel, (P + 127) / 128, 128, 0, st, w.bbox, dst_off, cell_size, P, w.params, w.sort_desc);
     R3D_LAUNCH(keys_kernel, dim3(pt_blocks, P), GB_THREADS, 0, st, dst, dst_off, w.params, w.keys[0], w.vals[0], w.max_dst);
-    for (int pass = 0; pass < 4; pass++) {
-        const int in = pass & 1, out = in ^ 1;
-        R3D_LAUNCH(rs_hist, dim3(w.tiles, P), GB_THREADS, 0, st, w.keys[in], w.params, w.hist, pass, w.max_dst, w.tiles);
-        R3D_LAUNCH(rs_scan, P, 1024, 0, st, w.hist, w.params, pass, w.tiles);
-        R3D_LAUNCH(rs_scatter, dim3(w.tiles, P), GB_THREADS, 0, st, w.keys[in], w.vals[in], w.keys[out], w.vals[out], w.hist,
-                   w.params, pass, w.max_dst, w.tiles);
-    }
+    int rc = radix_sort_pairs(w.keys, w.vals, w.hist, w.sort_desc, P, w.max_dst, w.tiles, st);
+    if (rc != R3D_OK) return rc;
     R3D_LAUNCH(gather_kernel, dim3(w.tiles, P), GB_THREADS, 0, st, w, dst, dst_off);
     R3D_LAUNCH(blocks_scan_kernel, P, 1024, 0, st, w);
     R3D_LAUNCH(blocks_assign_kernel, dim3(w.tiles, P), GB_THREADS, 0, st, w);
-    {
-        const int warps_per_cta = GB_THREADS / 32;
-        // a block holds at least one point, so max_dst bounds the block count; CTAs past the
-        // pair's n_blocks return immediately
-        R3D_LAUNCH(cell_table_kernel, dim3((w.max_dst + warps_per_cta - 1) / warps_per_cta, P), GB_THREADS, 0, st, w);
-    }
+    R3D_LAUNCH(cell_table_kernel, dim3(148, P), GB_THREADS, 0, st, w);
     return R3D_OK;
 }
 

@@ -40,6 +40,11 @@ struct GridParams {
     int pad;
 };
 
+struct SortDesc {             // per pair: how many keys, how many 8-bit radix passes they need
+    int n;
+    int n_passes;
+};
+
 struct GridView {             // raw pointers of one pair's grid
     const Point4* pts;        // sorted points (idx = position in the original cloud)
     const uint2* hash;        // {block_linear, block_id}
@@ -207,6 +212,7 @@ struct GridWorkspace {
     size_t hash_slots;              // per pair (power of two)
     unsigned long long* bbox;       // [pair][6] encoded min xyz, max xyz
     GridParams* params;             // [pair]
+    SortDesc* sort_desc;            // [pair]
     uint32_t* keys[2];              // [pair][max_dst]
     uint32_t* vals[2];
     uint32_t* hist;                 // [pair][256][tiles]
@@ -219,6 +225,9 @@ struct GridWorkspace {
 };
 
 size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_dst);
+int radix_sort_pairs(uint32_t* const keys[2], uint32_t* const vals[2], uint32_t* hist, const SortDesc* desc, int n_pairs,
+                     int cap, int tiles, cudaStream_t st);
+int radix_tiles(int cap);
 // Builds the grids of all pairs (async on `st`).  dst: xyzw points, offsets on device.
 int grid_build(const GridWorkspace& w, const Point4* dst, const int32_t* dst_off, double cell_size, cudaStream_t st);
 

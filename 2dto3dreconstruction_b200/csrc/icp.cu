@@ -1,9 +1,11 @@
 // K2 query + K3: the ICP loop of utils/icp.py:74-133, batched over pairs, entirely on the device.
 //
 // Per iteration (no host round trip; converged pairs turn into early-exit CTAs):
-//   nn_kernel        q = T_cum * a (fp64), exact NN on the sparse-block grid.  Iterations >= 2
-//                    seed the upper bound with the previous neighbour (the cloud moves little
-//                    between iterations, so the search box is ~1-2 cells wide).  With
+//   nn_kernel        q = T_cum * a (fp64), exact NN on the sparse-block grid, one warp per 32
+//                    spatially adjacent queries (coop_search.cuh; the source cloud is sorted by
+//                    cell key once, before the loop).  Iterations >= 2 seed the upper bound with
+//                    the previous neighbour (the cloud moves little between iterations, so the
+//                    search box is ~1-2 cells wider than the warp's footprint).  With
 //                    partial_set_size == 1 the 16 Kabsch moments are reduced in the same kernel.
 //   select_kernel    (partial < 1) radix-select of the cutoff-th smallest squared distance
 //                    = np.argpartition(distances, cutoff-1)[:cutoff], utils/icp.py:109-110
@@ -12,7 +14,8 @@
 //                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126)
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
-#include "grid.cuh"
+#include "coop_search.cuh"
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -35,11 +38,25 @@ struct PairState {
 
 struct IcpWorkspace {
     GridWorkspace grid;
-    int n_pairs, max_src, src_tiles;
+    int n_pairs, max_src, src_tiles, src_rows;
     PairState* state;      // [pair]
+    SortDesc* src_desc;    // [pair]
+    uint32_t* skeys[2];    // [pair][max_src]  source sort keys (ping-pong)
+    uint32_t* svals[2];    // [pair][max_src]
+    uint32_t* shist;       // [pair][256][src radix tiles]
+    int src_rtiles;
+    Point4* src_sorted;    // [pair][max_src]  source cloud in cell-key order, idx = original index
+    uint32_t* seg_tile_cnt; // [pair][seg_tiles]
+    int seg_tiles;
+    uint32_t* seg_start;   // [pair][max_src + 1]  first sorted query of every source block segment
+    int* n_seg;            // [pair]
+    uint32_t* grp;         // [pair][grp_cap]  query groups: (first sorted query << 6) | count
+    int grp_cap;
+    int* n_grp;            // [pair]
+    int nn_ctas;           // CTAs per pair of the persistent nn kernel
     int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
     double* d2;            // [pair][max_src]
-    double* partial;       // [pair][src_tiles][16]
+    double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
 };
 
@@ -47,12 +64,39 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     grid_workspace_layout(w.grid, a, n_pairs, max_dst);
     w.n_pairs = n_pairs;
     w.max_src = max_src;
-    w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;
+    w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
+    // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
+    w.src_rows = w.src_tiles * (NN_THREADS / 32);
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
+    w.src_desc = a.take<SortDesc>(P);
+    w.src_rtiles = radix_tiles(max_src);
+    for (int k = 0; k < 2; k++) {
+        w.skeys[k] = a.take<uint32_t>(P * max_src);
+        w.svals[k] = a.take<uint32_t>(P * max_src);
+    }
+    w.shist = a.take<uint32_t>(P * 256 * w.src_rtiles);
+    w.src_sorted = a.take<Point4>(P * max_src);
+    w.seg_tiles = (max_src + 2047) / 2048;
+    w.seg_tile_cnt = a.take<uint32_t>(P * w.seg_tiles);
+    w.seg_start = a.take<uint32_t>(P * ((size_t)max_src + 1));
+    w.n_seg = a.take<int>(P);
+    // worst case: every query alone in its block -> one group per query
+    w.grp_cap = max_src + 1;
+    w.grp = a.take<uint32_t>(P * (size_t)w.grp_cap);
+    w.n_grp = a.take<int>(P);
+    {
+        // persistent nn kernel: enough CTAs to fill 148 SMs x 8 resident CTAs over the chunk's pairs,
+        // never more than one warp per 32 queries
+        int per_pair = (148 * 8 + n_pairs - 1) / n_pairs;
+        const int cap = (max_src + NN_THREADS - 1) / NN_THREADS;
+        if (per_pair > cap) per_pair = cap;
+        if (per_pair < 1) per_pair = 1;
+        w.nn_ctas = per_pair;
+    }
     w.nn_pos = a.take<int32_t>(P * max_src);
     w.d2 = a.take<double>(P * max_src);
-    w.partial = a.take<double>(P * w.src_tiles * 16);
+    w.partial = a.take<double>(P * w.src_rows * 16);
     w.amom = a.take<double>(P * 16);
     return a.used;
 }
@@ -66,7 +110,7 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     for (int k = 0; k < 12; k++) s.T[k] = init_pose ? init_pose[(size_t)pair * 16 + k] : ((k % 5 == 0) ? 1.0 : 0.0);
     s.prev_err = 0.0;
     s.mean_err = 0.0;
-    s.tau = 0.0;
+    s.tau = CUDART_INF;      // keep everything until select_kernel says otherwise
     s.idx_cut = 0x7fffffff;
     s.iters = 1;
     s.done = 0;
@@ -75,25 +119,246 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     s.pad = 0;
     if (s.n_src <= 0 || w.grid.params[pair].n_pts <= 0) s.done = 1;
     w.state[pair] = s;
+    w.src_desc[pair].n = s.n_src > 0 ? s.n_src : 0;
+    w.src_desc[pair].n_passes = w.grid.params[pair].n_passes;
 }
 
-// ---- block reduction of 16 doubles per thread ----------------------------------------------------
-__device__ __forceinline__ void reduce16_store(const double (&m)[16], double* red /* [16][NN_THREADS] */,
-                                               double* __restrict__ out16) {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-#pragma unroll
-    for (int k = 0; k < 16; k++) red[k * NN_THREADS + t] = m[k];
+// ---- one-time spatial sort of the source cloud, and query groups ------------------------------------
+// key = (block << 6 | octant-major fine cell) of the destination-grid cell of the (initially posed)
+// source point, clamped into the grid.  Queries of one block (4x4x4 cells) are contiguous after the
+// sort and, inside a block, ordered octant by octant.  Groups of up to G consecutive queries are then
+// cut so that no group straddles two blocks: a group's queries are within one block edge of each
+// other, and rigid updates move them together, so the union box of a group stays a few cells wide
+// for every iteration.  (Cutting fixed-size chunks of a space-filling-curve order does not work for
+// a surface: consecutive occupied cells along the curve can be arbitrarily far apart -- measured
+// union boxes of up to the whole scene with a Hilbert order.)
+__global__ void __launch_bounds__(256)
+src_keys_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __restrict__ src_off) {
+    const int pair = blockIdx.y;
+    __shared__ GridParams g;
+    __shared__ double T[12];
+    __shared__ int s_n;
+    if (threadIdx.x == 0) { g = w.grid.params[pair]; s_n = w.state[pair].n_src; }
+    if (threadIdx.x < 12) T[threadIdx.x] = w.state[pair].T[threadIdx.x];
     __syncthreads();
-    constexpr int NW = NN_THREADS / 32;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= s_n) return;
+    const Point4 a = load_point(src + src_off[pair] + i);
+    const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
+    const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
+    const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
+    const int ix = cell_coord((qx - g.ox) * g.inv_cell, g.nx);
+    const int iy = cell_coord((qy - g.oy) * g.inv_cell, g.ny);
+    const int iz = cell_coord((qz - g.oz) * g.inv_cell, g.nz);
+    const uint32_t blk = (uint32_t)(((iz >> 2) * g.by + (iy >> 2)) * g.bx + (ix >> 2));
+    const uint32_t fine = (uint32_t)((((iz >> 1) & 1) << 5) | (((iy >> 1) & 1) << 4) | (((ix >> 1) & 1) << 3) |
+                                     ((iz & 1) << 2) | ((iy & 1) << 1) | (ix & 1));
+    w.skeys[0][(size_t)pair * w.max_src + i] = (blk << 6) | fine;
+    w.svals[0][(size_t)pair * w.max_src + i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+src_gather_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __restrict__ src_off) {
+    const int pair = blockIdx.y;
+    const int n = w.state[pair].n_src;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t* vals = w.svals[w.src_desc[pair].n_passes & 1] + (size_t)pair * w.max_src;
+    const uint32_t v = vals[i];
+    const Point4 a = load_point(src + src_off[pair] + v);
+    store_point(w.src_sorted + (size_t)pair * w.max_src + i, a.x, a.y, a.z, (int32_t)v);
+}
+
+// ---- query groups -----------------------------------------------------------------------------------
+constexpr int SEG_TILE = 2048;
+
+// segment = run of sorted source keys with the same block (key >> 6)
+__global__ void __launch_bounds__(256)
+seg_count_kernel(IcpWorkspace w) {
+    const int pair = blockIdx.y, tile = blockIdx.x;
+    const int n = w.state[pair].n_src;
+    if (tile * SEG_TILE >= n) return;
+    const uint32_t* keys = w.skeys[w.src_desc[pair].n_passes & 1] + (size_t)pair * w.max_src;
+    int c = 0;
 #pragma unroll
-    for (int j = 0; j < 16 / NW; j++) {
-        const int k = warp * (16 / NW) + j;
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < NW; c++) s += red[k * NN_THREADS + c * 32 + lane];
-        s = warp_sum(s);
-        if (lane == 0) out16[k] = s;
+    for (int r = 0; r < SEG_TILE / 256; r++) {
+        const int i = tile * SEG_TILE + r * 256 + threadIdx.x;
+        if (i < n) c += (i == 0) || ((keys[i - 1] >> 6) != (keys[i] >> 6));
     }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int sw[8];
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < 8; k++) t += sw[k];
+        w.seg_tile_cnt[(size_t)pair * w.seg_tiles + tile] = (uint32_t)t;
+    }
+}
+
+// exclusive scan of n (<= a few hundred thousand) uint32 by one CTA of 1024 threads; returns the total
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* data, int n) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < n; start += 1024) {
+        const int i = start + threadIdx.x;
+        const uint32_t v = (i < n) ? data[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t t = warp_tot[lane];
+            uint32_t ts = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
+                if (lane >= o) ts += y;
+            }
+            warp_tot[lane] = ts - t;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[warp] + x - v;
+        if (i < n) data[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    return carry;
+}
+
+__global__ void __launch_bounds__(1024)
+seg_scan_kernel(IcpWorkspace w) {
+    const int pair = blockIdx.x;
+    const int n = w.state[pair].n_src;
+    const int tiles = (n + SEG_TILE - 1) / SEG_TILE;
+    const uint32_t total = cta_exclusive_scan(w.seg_tile_cnt + (size_t)pair * w.seg_tiles, tiles);
+    if (threadIdx.x == 0) {
+        w.n_seg[pair] = (int)total;
+        w.seg_start[(size_t)pair * (w.max_src + 1) + total] = (uint32_t)n;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+seg_assign_kernel(IcpWorkspace w) {
+    const int pair = blockIdx.y, tile = blockIdx.x;
+    const int n = w.state[pair].n_src;
+    if (tile * SEG_TILE >= n) return;
+    const uint32_t* keys = w.skeys[w.src_desc[pair].n_passes & 1] + (size_t)pair * w.max_src;
+    constexpr int NW = 8, ROUNDS = SEG_TILE / 256;
+    __shared__ uint32_t cnt[ROUNDS * NW];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned ballots[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int i = tile * SEG_TILE + r * 256 + threadIdx.x;
+        bool st = false;
+        if (i < n) st = (i == 0) || ((keys[i - 1] >> 6) != (keys[i] >> 6));
+        ballots[r] = __ballot_sync(0xffffffffu, st);
+        if (lane == 0) cnt[r * NW + warp] = __popc(ballots[r]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t a = cnt[2 * lane], b = cnt[2 * lane + 1], sab = a + b;
+        uint32_t x = sab;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        cnt[2 * lane] = x - sab;
+        cnt[2 * lane + 1] = x - sab + a;
+    }
+    __syncthreads();
+    const uint32_t base = w.seg_tile_cnt[(size_t)pair * w.seg_tiles + tile];
+    uint32_t* seg_start = w.seg_start + (size_t)pair * (w.max_src + 1);
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        if (!((ballots[r] >> lane) & 1u)) continue;
+        const int i = tile * SEG_TILE + r * 256 + threadIdx.x;
+        seg_start[base + cnt[r * NW + warp] + __popc(ballots[r] & ((1u << lane) - 1u))] = (uint32_t)i;
+    }
+}
+
+// one CTA per pair: groups per segment = ceil(size / G); exclusive scan; write the group table.
+// entry = (first sorted query << 6) | count, count in 1..32
+__global__ void __launch_bounds__(1024)
+seg_groups_kernel(IcpWorkspace w, int G) {
+    const int pair = blockIdx.x;
+    const int nseg = w.n_seg[pair];
+    const uint32_t* seg_start = w.seg_start + (size_t)pair * (w.max_src + 1);
+    uint32_t* table = w.grp + (size_t)pair * w.grp_cap;
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < nseg; start += 1024) {
+        const int j = start + threadIdx.x;
+        uint32_t s0 = 0, sz = 0;
+        if (j < nseg) { s0 = seg_start[j]; sz = seg_start[j + 1] - s0; }
+        const uint32_t v = (sz + G - 1) / G;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t t = warp_tot[lane];
+            uint32_t ts = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
+                if (lane >= o) ts += y;
+            }
+            warp_tot[lane] = ts - t;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[warp] + x - v;
+        for (uint32_t k = 0; k < v; k++) {
+            const uint32_t first = s0 + k * G;
+            const uint32_t c = min((uint32_t)G, sz - k * G);
+            table[excl + k] = (first << 6) | c;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) w.n_grp[pair] = (int)carry;
+}
+
+// ---- per-warp reduction of 16 doubles per lane (no CTA barrier) --------------------------------------
+// `scratch` is >= 16*33 doubles of shared memory owned by the warp.  Rows are skewed by one double
+// so that the 16 row-summing lanes hit distinct banks.  Fixed summation order: deterministic.
+__device__ __forceinline__ double warp_reduce16(const double (&m)[16], double* scratch) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 16; k++) scratch[k * 33 + lane] = m[k];
+    __syncwarp();
+    const int row = lane & 15, half = lane >> 4;
+    const double* r = scratch + row * 33 + half * 16;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) s += r[j];
+    s += __shfl_down_sync(0xffffffffu, s, 16);
+    __syncwarp();
+    return s;      // lanes 0..15 hold the sum of moment `lane`
+}
+
+__device__ __forceinline__ void warp_reduce16_store(const double (&m)[16], double* scratch, double* __restrict__ out16) {
+    const double s = warp_reduce16(m, scratch);
+    if ((threadIdx.x & 31) < 16) out16[threadIdx.x & 31] = s;
 }
 
 __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, double ay, double az, double bx, double by,
@@ -107,55 +372,77 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
 }
 
 // ---- nearest neighbour ----------------------------------------------------------------------------
-template <bool SEEDED, bool FUSED>
+// Persistent kernel: grid (nn_ctas, pairs).  A warp repeatedly takes 32/G consecutive query groups.
+template <int G, bool SEEDED, bool FUSED>
 __global__ void __launch_bounds__(NN_THREADS)
-nn_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __restrict__ src_off, int write_d2) {
+nn_kernel(IcpWorkspace w, int write_d2) {
     const int pair = blockIdx.y;
+    constexpr int NGW = 32 / G;
     __shared__ GridParams g;
     __shared__ double T[12];
-    __shared__ int s_n, s_done;
-    __shared__ double red[FUSED ? 16 * NN_THREADS : 1];
+    __shared__ int s_ngrp, s_done;
+    __shared__ Point4 stage[NN_THREADS / 32][COOP_WARP_CAP];     // 6 KB per warp; reused as reduction scratch
     if (threadIdx.x == 0) {
         g = w.grid.params[pair];
-        s_n = w.state[pair].n_src;
+        s_ngrp = w.n_grp[pair];
         s_done = w.state[pair].done;
     }
     if (threadIdx.x < 12) T[threadIdx.x] = w.state[pair].T[threadIdx.x];
     __syncthreads();
-    if (s_done || blockIdx.x * NN_THREADS >= s_n) return;
-
+    if (s_done) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lg = lane & (G - 1);
     const GridView v = grid_view(w.grid, pair);
-    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
-    const bool active = i < s_n;
-    double m[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) m[k] = 0.0;
+    const uint32_t* table = w.grp + (size_t)pair * w.grp_cap;
+    const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
+    int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
+    double* d2_out = w.d2 + (size_t)pair * w.max_src;
+    const int n_tasks = (s_ngrp + NGW - 1) / NGW;
+    double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this warp's tasks
 
-    if (active) {
-        const Point4 a = load_point(src + src_off[pair] + i);
-        const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
-        const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
-        const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
+    for (int task = blockIdx.x * (NN_THREADS / 32) + warp; task < n_tasks; task += gridDim.x * (NN_THREADS / 32)) {
+        const int gid = task * NGW + lane / G;
+        bool active = false;
+        int i = 0;
+        if (gid < s_ngrp) {
+            const uint32_t e = __ldg(table + gid);
+            active = lg < (int)(e & 63u);
+            i = (int)(e >> 6) + lg;
+        }
+        double qx = 0.0, qy = 0.0, qz = 0.0;
         Best best;
         best.d2 = CUDART_INF;
         best.idx = 0x7fffffff;
         best.pos = 0;
-        int32_t* my_pos = w.nn_pos + (size_t)pair * w.max_src + i;
-        if (SEEDED) {
-            consider(best, v.pts, *my_pos, qx, qy, qz);
-        } else {
-            seed_search(best, v, g, qx, qy, qz);
+        if (active) {
+            const Point4 a = load_point(src + i);
+            qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
+            qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
+            qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
+            if (SEEDED) consider(best, v.pts, nn_pos[i], qx, qy, qz);
         }
-        bounded_search(best, v, g, qx, qy, qz);
-        *my_pos = best.pos;
-        if (!FUSED || write_d2) w.d2[(size_t)pair * w.max_src + i] = best.d2;
+        GroupStage<G> st;
+        st.buf = stage[warp] + (lane / G) * GroupStage<G>::CAP;
+        st.n = 0;
+        coop_search<G>(st, best, v, g, active, qx, qy, qz);
+        if (active) {
+            nn_pos[i] = best.pos;
+            if (!FUSED || write_d2) d2_out[i] = best.d2;
+        }
         if (FUSED) {
-            const Point4 b = load_point(v.pts + best.pos);
-            accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
-                            b.z - g.shift[2], sqrt(best.d2));
+            double m[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) m[k] = 0.0;
+            if (active) {
+                const Point4 b = load_point(v.pts + best.pos);
+                accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
+                                b.z - g.shift[2], sqrt(best.d2));
+            }
+            acc += warp_reduce16(m, reinterpret_cast<double*>(stage[warp]));
         }
     }
-    if (FUSED) reduce16_store(m, red, w.partial + ((size_t)pair * w.src_tiles + blockIdx.x) * 16);
+    // every warp of the grid writes its row (zeros if it had no task): solve_kernel sums them all
+    if (FUSED && lane < 16)
+        w.partial[((size_t)pair * w.src_rows + (size_t)(blockIdx.x * (NN_THREADS / 32) + warp)) * 16 + lane] = acc;
 }
 
 // ---- partial-set selection ---------------------------------------------------------------------------
@@ -259,12 +546,12 @@ __device__ __forceinline__ bool kept(double d2, int i, double tau, int idx_cut) 
 }
 
 __global__ void __launch_bounds__(NN_THREADS)
-moments_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __restrict__ src_off) {
+moments_kernel(IcpWorkspace w) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
     __shared__ double T[12];
     __shared__ PairState s;
-    __shared__ double red[16 * NN_THREADS];
+    __shared__ double red[NN_THREADS / 32][16 * 33];
     if (threadIdx.x == 0) { g = w.grid.params[pair]; s = w.state[pair]; }
     __syncthreads();
     if (threadIdx.x < 12) T[threadIdx.x] = s.T[threadIdx.x];
@@ -277,7 +564,7 @@ moments_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __
     if (i < s.n_src) {
         const double d2 = w.d2[(size_t)pair * w.max_src + i];
         if (kept(d2, i, s.tau, s.idx_cut)) {
-            const Point4 a = load_point(src + src_off[pair] + i);
+            const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
             const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
             const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
             const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
@@ -286,36 +573,47 @@ moments_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __
                             b.z - g.shift[2], sqrt(d2));
         }
     }
-    reduce16_store(m, red, w.partial + ((size_t)pair * w.src_tiles + blockIdx.x) * 16);
+    warp_reduce16_store(m, red[threadIdx.x >> 5],
+                        w.partial + ((size_t)pair * w.src_rows + (size_t)(blockIdx.x * (NN_THREADS / 32) + (threadIdx.x >> 5))) * 16);
 }
 
 // ---- solve ---------------------------------------------------------------------------------------------
-// Sum `count` rows of 16 doubles in a fixed order with 128 threads; result in out16 (shared).
-__device__ __forceinline__ void sum_rows16(const double* __restrict__ rows, int count, double* sm /* [8][16] */, double* out16) {
-    const int q = threadIdx.x & 15, grp = threadIdx.x >> 4;   // 8 groups
-    double s = 0.0;
-    for (int r = grp; r < count; r += 8) s += rows[(size_t)r * 16 + q];
-    sm[grp * 16 + q] = s;
+// Sum `count` rows of 16 doubles in a fixed order with SOLVE_THREADS threads; result in out16 (shared).
+constexpr int SOLVE_THREADS = 512;
+__device__ __forceinline__ void sum_rows16(const double* __restrict__ rows, int count, double* sm /* [SOLVE_THREADS] */,
+                                           double* out16) {
+    constexpr int NGRP = SOLVE_THREADS / 16;
+    const int q = threadIdx.x & 15, grp = threadIdx.x >> 4;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // four independent chains hide the load latency
+    int r = grp;
+    for (; r + 3 * NGRP < count; r += 4 * NGRP) {
+        s0 += rows[(size_t)r * 16 + q];
+        s1 += rows[(size_t)(r + NGRP) * 16 + q];
+        s2 += rows[(size_t)(r + 2 * NGRP) * 16 + q];
+        s3 += rows[(size_t)(r + 3 * NGRP) * 16 + q];
+    }
+    for (; r < count; r += NGRP) s0 += rows[(size_t)r * 16 + q];
+    sm[grp * 16 + q] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (threadIdx.x < 16) {
         double t = 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) t += sm[k * 16 + threadIdx.x];
+        for (int k = 0; k < NGRP; k++) t += sm[k * 16 + threadIdx.x];
         out16[threadIdx.x] = t;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(128)
-solve_kernel(IcpWorkspace w, double tolerance) {
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     const int pair = blockIdx.x;
     PairState* st = w.state + pair;
     if (st->done) return;
-    __shared__ double sm[8 * 16];
+    __shared__ double sm[SOLVE_THREADS];
     __shared__ double m[16];
     const int n = st->n_src;
-    const int tiles = (n + NN_THREADS - 1) / NN_THREADS;
-    sum_rows16(w.partial + (size_t)pair * w.src_tiles * 16, tiles, sm, m);
+    // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
+    const int rows = rows_fixed > 0 ? rows_fixed : (n + 31) / 32;
+    sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
         const double cnt = (double)st->cutoff;
@@ -343,9 +641,9 @@ solve_kernel(IcpWorkspace w, double tolerance) {
 
 // ---- moments of A and the final fit -----------------------------------------------------------------------
 __global__ void __launch_bounds__(NN_THREADS)
-src_moments_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* __restrict__ src_off) {
+src_moments_kernel(IcpWorkspace w) {
     const int pair = blockIdx.y;
-    __shared__ double red[16 * NN_THREADS];
+    __shared__ double red[NN_THREADS / 32][16 * 33];
     __shared__ double shift[3];
     __shared__ int s_n;
     if (threadIdx.x == 0) {
@@ -359,22 +657,23 @@ src_moments_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t
 #pragma unroll
     for (int k = 0; k < 16; k++) m[k] = 0.0;
     if (i < s_n) {
-        const Point4 a = load_point(src + src_off[pair] + i);
+        const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
         const double x = a.x - shift[0], y = a.y - shift[1], z = a.z - shift[2];
         m[0] = x; m[1] = y; m[2] = z;
         m[3] = x * x; m[4] = x * y; m[5] = x * z; m[6] = y * y; m[7] = y * z; m[8] = z * z;
     }
-    reduce16_store(m, red, w.partial + ((size_t)pair * w.src_tiles + blockIdx.x) * 16);
+    warp_reduce16_store(m, red[threadIdx.x >> 5],
+                        w.partial + ((size_t)pair * w.src_rows + (size_t)(blockIdx.x * (NN_THREADS / 32) + (threadIdx.x >> 5))) * 16);
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SOLVE_THREADS)
 src_moments_reduce_kernel(IcpWorkspace w) {
     const int pair = blockIdx.x;
-    __shared__ double sm[8 * 16];
+    __shared__ double sm[SOLVE_THREADS];
     __shared__ double m[16];
     const int n = w.state[pair].n_src;
-    const int tiles = (n + NN_THREADS - 1) / NN_THREADS;
-    sum_rows16(w.partial + (size_t)pair * w.src_tiles * 16, tiles, sm, m);
+    const int rows = (n + 31) / 32;
+    sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x < 16) w.amom[(size_t)pair * 16 + threadIdx.x] = m[threadIdx.x];
 }
 
@@ -419,7 +718,16 @@ export_kernel(IcpWorkspace w, const int32_t* __restrict__ src_off, int32_t* __re
     const int n = st.n_src;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    const size_t o = (size_t)src_off[pair] + i;
+    if (w.grid.params[pair].n_pts <= 0) {     // empty destination cloud: nothing to match
+        const size_t o = (size_t)src_off[pair] + i;
+        if (out_idx) out_idx[o] = -1;
+        if (out_dist) out_dist[o] = CUDART_INF;
+        if (out_keep) out_keep[o] = 0;
+        return;
+    }
+    // i runs over the SORTED source order; results go back to the caller's order
+    const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
+    const size_t o = (size_t)src_off[pair] + a.idx;
     const double d2 = w.d2[(size_t)pair * w.max_src + i];
     if (out_idx) {
         const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + w.nn_pos[(size_t)pair * w.max_src + i]);
@@ -460,6 +768,43 @@ struct NnTimer {
 };
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
+static std::atomic<int> g_group_size{8};
+
+template <int G>
+static int launch_nn_g(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+    if (seeded) {
+        if (fused) R3D_LAUNCH((nn_kernel<G, true, true>), grid, NN_THREADS, 0, st, w, write_d2);
+        else R3D_LAUNCH((nn_kernel<G, true, false>), grid, NN_THREADS, 0, st, w, write_d2);
+    } else {
+        if (fused) R3D_LAUNCH((nn_kernel<G, false, true>), grid, NN_THREADS, 0, st, w, write_d2);
+        else R3D_LAUNCH((nn_kernel<G, false, false>), grid, NN_THREADS, 0, st, w, write_d2);
+    }
+    return R3D_OK;
+}
+
+static int launch_nn(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+    switch (g_group_size.load()) {
+        case 32: return launch_nn_g<32>(w, grid, seeded, fused, write_d2, st);
+        case 16: return launch_nn_g<16>(w, grid, seeded, fused, write_d2, st);
+        default: return launch_nn_g<8>(w, grid, seeded, fused, write_d2, st);
+    }
+}
+
+static int sort_source(IcpWorkspace& w, const Point4* src, const int32_t* src_off, cudaStream_t st) {
+    const dim3 g256((w.max_src + 255) / 256, w.n_pairs);
+    R3D_LAUNCH(src_keys_kernel, g256, 256, 0, st, w, src, src_off);
+    int rc = radix_sort_pairs(w.skeys, w.svals, w.shist, w.src_desc, w.n_pairs, w.max_src, w.src_rtiles, st);
+    if (rc != R3D_OK) return rc;
+    R3D_LAUNCH(src_gather_kernel, g256, 256, 0, st, w, src, src_off);
+    // query groups (never straddling a block)
+    const dim3 gseg(w.seg_tiles, w.n_pairs);
+    R3D_LAUNCH(seg_count_kernel, gseg, 256, 0, st, w);
+    R3D_LAUNCH(seg_scan_kernel, w.n_pairs, 1024, 0, st, w);
+    R3D_LAUNCH(seg_assign_kernel, gseg, 256, 0, st, w);
+    R3D_LAUNCH(seg_groups_kernel, w.n_pairs, 1024, 0, st, w, g_group_size.load());
+    return R3D_OK;
+}
+
 int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Point4* dst, const int32_t* dst_off,
             const double* init_pose, const r3d_icp_params& prm, double* T_out, int32_t* iters_out, double* mean_err_out,
             int32_t* last_idx, double* last_dist, uint8_t* last_keep, cudaStream_t st) {
@@ -468,26 +813,24 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(state_init_kernel, (P + 127) / 128, 128, 0, st, w, src_off, init_pose, prm.partial_set_size);
     const dim3 qgrid(w.src_tiles, P);
-    R3D_LAUNCH(src_moments_kernel, qgrid, NN_THREADS, 0, st, w, src, src_off);
-    R3D_LAUNCH(src_moments_reduce_kernel, P, 128, 0, st, w);
-    const bool fused = prm.partial_set_size >= 1.0;
+    const dim3 nngrid(w.nn_ctas, P);
+    rc = sort_source(w, src, src_off, st);
+    if (rc != R3D_OK) return rc;
+    R3D_LAUNCH(src_moments_kernel, qgrid, NN_THREADS, 0, st, w);
+    R3D_LAUNCH(src_moments_reduce_kernel, P, SOLVE_THREADS, 0, st, w);
+    const bool fused = prm.partial_set_size >= 1.0 && !getenv("R3D_FORCE_UNFUSED");
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
     for (int it = 0; it < prm.max_iterations; it++) {
         {
             NnTimer timer(st);
-            if (fused) {
-                if (it == 0) R3D_LAUNCH((nn_kernel<false, true>), qgrid, NN_THREADS, 0, st, w, src, src_off, want_d2);
-                else R3D_LAUNCH((nn_kernel<true, true>), qgrid, NN_THREADS, 0, st, w, src, src_off, want_d2);
-            } else {
-                if (it == 0) R3D_LAUNCH((nn_kernel<false, false>), qgrid, NN_THREADS, 0, st, w, src, src_off, 1);
-                else R3D_LAUNCH((nn_kernel<true, false>), qgrid, NN_THREADS, 0, st, w, src, src_off, 1);
-            }
+            rc = launch_nn(w, nngrid, it > 0, fused, fused ? want_d2 : 1, st);
+            if (rc != R3D_OK) return rc;
         }
         if (!fused) {
             R3D_LAUNCH(select_kernel, P, 1024, 0, st, w);
-            R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w, src, src_off);
+            R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
         }
-        R3D_LAUNCH(solve_kernel, P, 128, 0, st, w, prm.tolerance);
+        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? w.nn_ctas * (NN_THREADS / 32) : 0);
     }
     R3D_LAUNCH(final_kernel, (P + 63) / 64, 64, 0, st, w, T_out, iters_out, mean_err_out);
     if ((last_idx || last_dist || last_keep) && prm.max_iterations > 0) {
@@ -516,9 +859,12 @@ int nn_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Poi
     int rc = grid_build(w.grid, dst, dst_off, cell_size, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(state_init_kernel, (P + 127) / 128, 128, 0, st, w, src_off, (const double*)nullptr, 1.0);
+    rc = sort_source(w, src, src_off, st);
+    if (rc != R3D_OK) return rc;
     {
         NnTimer timer(st);
-        R3D_LAUNCH((nn_kernel<false, false>), dim3(w.src_tiles, P), NN_THREADS, 0, st, w, src, src_off, 1);
+        rc = launch_nn(w, dim3(w.nn_ctas, P), false, false, 1, st);
+        if (rc != R3D_OK) return rc;
     }
     R3D_LAUNCH(export_kernel, dim3((w.max_src + 255) / 256, P), 256, 0, st, w, src_off, out_idx, out_dist, (uint8_t*)nullptr, 1);
     return R3D_OK;
@@ -586,4 +932,17 @@ extern "C" int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* 
     if (queries) *queries = 0;
     if (reset) g_time_used = 0;
     return R3D_OK;
+}
+
+extern "C" int r3d_set_option(int option, double value) {
+    switch (option) {
+        case R3D_OPT_GROUP_SIZE: {
+            const int gsz = (int)value;
+            if (gsz != 8 && gsz != 16 && gsz != 32) return R3D_ERR_INVALID;
+            g_group_size.store(gsz);
+            return R3D_OK;
+        }
+        default:
+            return R3D_ERR_INVALID;
+    }
 }

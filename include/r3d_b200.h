@@ -200,6 +200,11 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
                                   int32_t* n_src_out_host, int32_t* n_dst_out_host,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* Tuning knobs; none of them changes results.  R3D_OPT_GROUP_SIZE: lanes that share one staged
+ * candidate list in the NN search (8, 16 or 32; default 8). */
+typedef enum { R3D_OPT_GROUP_SIZE = 1 } r3d_option;
+int r3d_set_option(int option, double value);
+
 /* Number of kernels this library has launched since load (all entry points). */
 uint64_t r3d_launch_count(void);
 

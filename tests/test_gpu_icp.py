@@ -70,7 +70,12 @@ def test_full_density_pair(partial):
     Tr, dr, itr = O.icp(A, B, max_iterations=5, tolerance=0.0, partial_set_size=partial)
     assert it == itr == 6
     assert_transform_parity(T, Tr, O.scene_extent(B), "full pair")
-    np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=1e-6, atol=1e-6)
+    # Quantised depth makes exact distance ties real (45 of 276k queries in iteration 1 of this pair):
+    # the KD-tree and the lowest-index rule pick different, equally near points there, which moves
+    # the transforms by ~1e-6 and the final distances by ~1e-4.  Both are inside north_star's
+    # tolerance (1e-4 on R, 1e-4 x extent on t); the distances are checked at that scale.
+    assert dist.shape == dr.shape
+    np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=0, atol=1e-4 * O.scene_extent(B))
 
 
 def test_batch_matches_single_and_is_deterministic():
@@ -115,3 +120,34 @@ def test_zero_iterations_and_identity():
     assert it == itr
     np.testing.assert_allclose(T, np.eye(4), atol=1e-12)
     assert np.all(dist == 0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 127, 129, 4097, 20000])
+@pytest.mark.parametrize("partial", [1.0, 0.75])
+def test_one_iteration_consistency_over_sizes(n, partial):
+    """The transform of one iteration must be the Kabsch fit of the exported correspondences, for
+    source sizes around every tiling boundary (a partial-sum buffer overflow once hid here)."""
+    ops = sub("ops")
+    C = sub("_capi")
+    a, b = O.synth_depth_pair(5, h=240, w=320)
+    fa = np.zeros((480, 640), np.uint16)
+    fb = np.zeros((480, 640), np.uint16)
+    fa[120:360, 160:480] = a
+    fb[120:360, 160:480] = b
+    A, B = O.depth_to_voxel_ld(fa)[:n], O.depth_to_voxel_ld(fb)
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    r = ops.icp_batch(s, ops._offsets([len(A)]), d, ops._offsets([len(B)]), 1, len(A), len(B), max_iterations=1,
+                      tolerance=0.0, partial_set_size=partial, want_last=True)
+    keep = r["keep"].cpu().numpy().astype(bool)
+    idx = r["idx"].cpu().numpy()
+    cutoff = int(n * partial)
+    assert keep.sum() == cutoff
+    if cutoff < 3:
+        return      # under-determined fit: only the bookkeeping is checked
+    db, ib = O.nearest_neighbor_brute(A, B)
+    assert np.array_equal(idx, ib)
+    T_iter = O.best_fit_transform(A[keep], B[idx[keep]])
+    moved = (T_iter[:3, :3] @ A.T).T + T_iter[:3, 3]
+    T_want = O.best_fit_transform(A, moved)               # utils/icp.py:131
+    assert_transform_parity(r["T"][0].cpu().numpy(), T_want, O.scene_extent(B), "n=%d" % n, 1e-8, 1e-9)
