@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + (["-DR3D_NN_MIN_CTAS=" + os.environ["R3D_NN_MIN_CTAS"]] if os.environ.get("R3D_NN_MIN_CTAS") else [])
 
 
 def _nvcc():

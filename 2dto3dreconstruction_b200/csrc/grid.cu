@@ -6,6 +6,8 @@
 
 namespace r3d {
 
+std::atomic<double> g_cell_factor{2.0};   // automatic cell size = factor x estimated point spacing
+
 constexpr int GB_THREADS = 256;
 constexpr int RS_ROUNDS = 8;
 constexpr int RS_TILE = GB_THREADS * RS_ROUNDS;    // 2048 keys per tile
@@ -54,7 +56,8 @@ __device__ inline int bits_for(unsigned long long count) {   // bits needed to i
 }
 
 __global__ void plan_kernel(const unsigned long long* __restrict__ bbox, const int32_t* __restrict__ dst_off,
-                            double cell_size, int n_pairs, GridParams* __restrict__ params, SortDesc* __restrict__ desc) {
+                            double cell_size, double cell_factor, int n_pairs, GridParams* __restrict__ params,
+                            SortDesc* __restrict__ desc) {
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= n_pairs) return;
     GridParams g;
@@ -69,9 +72,10 @@ __global__ void plan_kernel(const unsigned long long* __restrict__ bbox, const i
     double c = cell_size;
     if (!(c > 0.0) || !isfinite(c)) {
         // automatic: depth-image clouds are surfaces; with N points over the largest bbox face the
-        // mean spacing is sqrt(area / N).  1.5 spacings per cell gives ~2 points per occupied cell.
+        // mean spacing is sqrt(area / N).  cell_factor spacings per cell (default 1.5: ~2 points per
+        // occupied cell).
         double face = fmax(e[0] * e[1], fmax(e[0] * e[2], e[1] * e[2]));
-        c = 1.5 * sqrt(face / (double)max(g.n_pts, 1));
+        c = cell_factor * sqrt(face / (double)max(g.n_pts, 1));
         if (!(c > 0.0) || !isfinite(c)) {
             double emax = fmax(e[0], fmax(e[1], e[2]));
             c = (emax > 0.0) ? emax / 64.0 : 1.0;
@@ -482,7 +486,8 @@ int grid_build(const GridWorkspace& w, const Point4* dst, const int32_t* dst_off
         int bx = pt_blocks < 64 ? pt_blocks : 64;
         R3D_LAUNCH(bbox_kernel, dim3(bx, P), GB_THREADS, 0, st, dst, dst_off, w.bbox);
     }
-    R3D_LAUNCH(plan_kernel, (P + 127) / 128, 128, 0, st, w.bbox, dst_off, cell_size, P, w.params, w.sort_desc);
+    R3D_LAUNCH(plan_kernel, (P + 127) / 128, 128, 0, st, w.bbox, dst_off, cell_size, g_cell_factor.load(), P, w.params,
+               w.sort_desc);
     R3D_LAUNCH(keys_kernel, dim3(pt_blocks, P), GB_THREADS, 0, st, dst, dst_off, w.params, w.keys[0], w.vals[0], w.max_dst);
     int rc = radix_sort_pairs(w.keys, w.vals, w.hist, w.sort_desc, P, w.max_dst, w.tiles, st);
     if (rc != R3D_OK) return rc;

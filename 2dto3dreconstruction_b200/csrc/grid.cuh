@@ -228,6 +228,7 @@ size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_ds
 int radix_sort_pairs(uint32_t* const keys[2], uint32_t* const vals[2], uint32_t* hist, const SortDesc* desc, int n_pairs,
                      int cap, int tiles, cudaStream_t st);
 int radix_tiles(int cap);
+extern std::atomic<double> g_cell_factor;
 // Builds the grids of all pairs (async on `st`).  dst: xyzw points, offsets on device.
 int grid_build(const GridWorkspace& w, const Point4* dst, const int32_t* dst_off, double cell_size, cudaStream_t st);
 

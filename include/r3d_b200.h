@@ -201,8 +201,9 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tuning knobs; none of them changes results.  R3D_OPT_GROUP_SIZE: lanes that share one staged
- * candidate list in the NN search (8, 16 or 32; default 8). */
-typedef enum { R3D_OPT_GROUP_SIZE = 1 } r3d_option;
+ * candidate list in the NN search (8, 16 or 32).  R3D_OPT_CELL_FACTOR: automatic grid cell edge in
+ * units of the estimated point spacing (used when cell_size <= 0). */
+typedef enum { R3D_OPT_GROUP_SIZE = 1, R3D_OPT_CELL_FACTOR = 2 } r3d_option;
 int r3d_set_option(int option, double value);
 
 /* Number of kernels this library has launched since load (all entry points). */

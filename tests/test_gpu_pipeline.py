@@ -1,0 +1,84 @@
+"""Fused batched registration (K1 -> grid -> ICP) vs the per-pair drop-ins and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import sub
+from oracle import ref_port as O
+from parity import assert_transform_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs(n, h=480, w=640, first=20):
+    fa, fb = [], []
+    for k in range(n):
+        a, b = O.synth_depth_pair(first + k, h=h, w=w)
+        fa.append(a)
+        fb.append(b)
+    return np.stack(fa), np.stack(fb)
+
+
+def test_device_and_host_paths_agree_with_drop_ins():
+    import torch
+    pipeline = sub("pipeline")
+    icp = sub("utils.icp")
+    fa, fb = _pairs(5, h=120, w=160)
+    big_a = np.zeros((5, 480, 640), np.uint16)
+    big_b = np.zeros((5, 480, 640), np.uint16)
+    big_a[:, 180:300, 240:400] = fa
+    big_b[:, 180:300, 240:400] = fb
+    big_a[3] = 0                                  # an empty source frame in the middle of the batch
+    kw = dict(max_iterations=8, tolerance=0.0, partial_set_size=1.0, pairs_per_chunk=2, n_streams=2)
+    dev = pipeline.register_depth_pairs(torch.from_numpy(big_a).cuda(), torch.from_numpy(big_b).cuda(), **kw)
+    host = pipeline.register_depth_pairs(big_a, big_b, **kw)
+    Td = dev["T"].cpu().numpy()
+    assert np.array_equal(Td, host["T"])
+    assert np.array_equal(dev["iters"].cpu().numpy(), host["iters"])
+    assert np.array_equal(dev["n_src"].cpu().numpy(), host["n_src"])
+    for p in (0, 1, 2, 4):
+        A, B = O.depth_to_voxel_ld(big_a[p]), O.depth_to_voxel_ld(big_b[p])
+        assert host["n_src"][p] == len(A) and host["n_dst"][p] == len(B)
+        T, dist, it = icp.icp(A, B, max_iterations=8, tolerance=0.0)
+        assert np.array_equal(T, Td[p]), "batched and single-pair paths must be bitwise identical"
+        Tr, _, itr = O.icp(A, B, max_iterations=8, tolerance=0.0)
+        assert it == itr == int(host["iters"][p])
+        assert_transform_parity(Td[p], Tr, O.scene_extent(B), "pair %d" % p, 1e-6, 1e-7)
+    assert host["n_src"][3] == 0
+
+
+def test_full_size_pairs_partial():
+    pipeline = sub("pipeline")
+    fa, fb = _pairs(3)
+    out = pipeline.register_depth_pairs(fa, fb, max_iterations=4, tolerance=0.0, partial_set_size=0.7, pairs_per_chunk=3,
+                                        n_streams=1)
+    for p in range(3):
+        A, B = O.depth_to_voxel_ld(fa[p]), O.depth_to_voxel_ld(fb[p])
+        Tr, _, itr = O.icp(A, B, max_iterations=4, tolerance=0.0, partial_set_size=0.7)
+        assert int(out["iters"][p]) == itr
+        assert_transform_parity(out["T"][p], Tr, O.scene_extent(B), "pair %d" % p)
+
+
+def test_chunking_does_not_change_results():
+    pipeline = sub("pipeline")
+    fa, fb = _pairs(7, h=96, w=128)
+    big_a = np.zeros((7, 480, 640), np.uint16)
+    big_b = np.zeros((7, 480, 640), np.uint16)
+    big_a[:, 192:288, 256:384] = fa
+    big_b[:, 192:288, 256:384] = fb
+    ref = None
+    for ppc, ns in [(1, 1), (3, 2), (7, 1), (16, 3)]:
+        out = pipeline.register_depth_pairs(big_a, big_b, max_iterations=6, tolerance=1e-3, pairs_per_chunk=ppc, n_streams=ns)
+        if ref is None:
+            ref = out
+        else:
+            assert np.array_equal(out["T"], ref["T"]) and np.array_equal(out["iters"], ref["iters"])
+
+
+def test_chain_matches_reference_prefix_product():
+    pipeline = sub("pipeline")
+    rec = sub("reconstruct")
+    rng = np.random.default_rng(0)
+    Ts = np.stack([np.eye(4) + rng.normal(size=(4, 4)) * 0.01 for _ in range(6)])
+    want = O.chain_prefix(list(Ts))
+    assert np.array_equal(pipeline.chain(Ts), np.stack(want))
+    assert all(np.array_equal(a, b) for a, b in zip(rec.chain_prefix(list(Ts)), want))

@@ -1,0 +1,157 @@
+"""K4 parity: 2-D homography RANSAC scoring (reference-exact) and 3-D hypothesis scoring."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, sub
+from oracle import ref_port as O
+
+pytestmark = pytest.mark.gpu
+
+
+class KP:
+    def __init__(self, x, y):
+        self.pt = (float(x), float(y))
+
+
+def test_q9_pieces_golden():
+    q9 = sub("utils.homography_utils.q9")
+    g = load_golden("ransac2d")
+    Hh, Ww = g["img_shape"]
+    orig = g["xy1"][:, ::-1].copy()
+    prime = g["xy2"][:, ::-1].copy()
+    binned = q9.make_binned_array((Hh, Ww), prime)
+    assert len(binned) == Hh and len(binned[0]) == Ww
+    for k in range(3):
+        tp = q9.get_transformed_points(orig, g["Hs"][k])
+        np.testing.assert_allclose(tp, g["tp%d" % k], rtol=1e-13, atol=1e-11)
+        m, s = q9.get_ssd_v2(orig, g["tp%d" % k], prime, binned)
+        assert np.array_equal(m, g["m%d" % k])
+        np.testing.assert_allclose(s, g["s%d" % k], rtol=1e-12, atol=0)
+
+
+def test_scoring_counts_match_oracle_for_many_hypotheses():
+    ops = sub("ops")
+    g = load_golden("ransac2d")
+    shape = tuple(g["img_shape"])
+    orig = g["xy1"][:, ::-1].copy()
+    prime = g["xy2"][:, ::-1].copy()
+    np.random.seed(11)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        Hs, _ = O.ransac_hypotheses(g["xy1"], g["xy2"], g["bf"], n_iter=60)
+        binned = O.make_binned_array(shape, prime)
+        want, want_m = [], []
+        for H in Hs:
+            tp = O.q9_get_transformed_points(orig, H)
+            m, s = O.get_ssd_v2(orig, tp, prime, binned)
+            want.append(len(m))
+            want_m.append(m)
+    counts, flags, mj, ms = ops.ransac2d_score(Hs, orig, prime, shape, want_matches=True)
+    counts = counts.cpu().numpy()
+    assert np.array_equal(counts, np.array(want)), "inlier counts must match exactly"
+    mj = mj.cpu().numpy()
+    for h in (0, int(np.argmax(want)), 59):
+        i = np.nonzero(mj[h] >= 0)[0]
+        got = np.stack((i, mj[h][i]), axis=1) if len(i) else np.zeros((0, 2), int)
+        ref = want_m[h] if len(want_m[h]) else np.zeros((0, 2), int)
+        assert np.array_equal(got, ref)
+
+
+def test_ransac_loop_golden_seeded():
+    q9 = sub("utils.homography_utils.q9")
+    g = load_golden("ransac2d")
+    kp1 = [KP(*p) for p in g["xy1"]]
+    kp2 = [KP(*p) for p in g["xy2"]]
+    img = np.zeros(tuple(g["img_shape"]), np.uint8)
+    np.random.seed(7)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        H, fm = q9.ransac_loop(img, img, kp1, kp2, g["bf"])
+    after = np.random.randint(1 << 30)
+    assert np.array_equal(fm, g["final_matches"])
+    np.testing.assert_allclose(H, g["H_final"], rtol=1e-9, atol=1e-12)
+    # the global RNG must have been consumed exactly as the reference consumes it
+    np.random.seed(7)
+    for _ in range(100):
+        np.random.randint(len(g["bf"]), size=4)
+    assert after == np.random.randint(1 << 30)
+
+
+def test_binned_array_wrap_and_errors():
+    q9 = sub("utils.homography_utils.q9")
+    kp2 = np.array([[0.4, 0.7], [30.2, 0.2], [10.5, 20.5]])        # first two wrap to the last row/col
+    tp = np.array([[118.5, 158.2], [29.0, 158.9], [10.0, 20.0], [np.nan, 1.0]])
+    binned = q9.make_binned_array((120, 160), kp2)
+    with pytest.raises(ValueError):
+        q9.get_ssd_v2(tp, tp, kp2, binned)
+    m, s = q9.get_ssd_v2(tp[:3], tp[:3], kp2, binned)
+    mo, so = O.get_ssd_v2(tp[:3], tp[:3], kp2, O.make_binned_array((120, 160), kp2))
+    assert np.array_equal(m, mo)
+    with pytest.raises(IndexError):
+        q9.make_binned_array((120, 160), np.array([[130.0, 5.0]]))
+    # a homography with w == 0 for some keypoint: the reference dies in int(); so do we
+    H = np.array([[1.0, 0, 0], [0, 1, 0], [0, 0, 0]])
+    with pytest.raises((ValueError, OverflowError)):
+        sub("ops")
+        counts, flags, _, _ = sub("ops").ransac2d_score(H[None], tp[:3], kp2, (120, 160))
+        q9._raise_for_flags(flags.cpu().numpy())
+
+
+def test_complex_homography_matches_numpy():
+    """numpy.linalg.eig can hand q9 a complex H; only the final assignment drops the imaginary part."""
+    q9 = sub("utils.homography_utils.q9")
+    g = load_golden("ransac2d")
+    Hc = g["dlt_H"]
+    k = int(np.argmax(np.abs(np.imag(Hc)).reshape(len(Hc), -1).max(axis=1)))
+    assert np.abs(np.imag(Hc[k])).max() > 0
+    orig = g["xy1"][:, ::-1].copy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = O.q9_get_transformed_points(orig, Hc[k])
+    got = q9.get_transformed_points(orig, Hc[k])
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["rigid", "affine"])
+def test_ransac3d_counts(kind):
+    ops = sub("ops")
+    import torch
+    rng = np.random.default_rng(11)
+    n = 5000
+    P = rng.uniform(-1000, 1000, (n, 3)).astype(np.float32).astype(np.float64)
+    ang = 0.2
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    T[:3, 3] = [15, -8, 5]
+    Q = O.get_transformed_points(P, T) + rng.normal(size=(n, 3))
+    out = rng.random(n) < 0.4
+    Q[out] = rng.uniform(-1000, 1000, (out.sum(), 3))
+    samples = np.random.RandomState(12345).randint(n, size=(300, 3 if kind == "rigid" else 4))
+    samples[:5] = np.nonzero(~out)[0][:5 * samples.shape[1]].reshape(5, -1)     # some all-inlier samples
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        hyps = O.rigid_hypotheses(P, Q, samples) if kind == "rigid" else O.affine_hypotheses(P, Q, samples)
+    hyps = np.concatenate((hyps, T[None]))
+    want = O.score_hypotheses_3d(hyps, P, Q)
+    got = ops.ransac3d_score(torch.from_numpy(hyps).cuda(), ops.pack_xyzw(torch.from_numpy(P).cuda()),
+                             ops.pack_xyzw(torch.from_numpy(Q).cuda())).cpu().numpy()
+    assert want[-1] > 0.4 * n
+    assert np.array_equal(got, want)
+
+
+def test_ransac3d_ragged_sizes():
+    ops = sub("ops")
+    import torch
+    rng = np.random.default_rng(3)
+    for n, nh in [(1, 1), (511, 3), (513, 129), (4097, 1000)]:
+        P = rng.normal(size=(n, 3)) * 3
+        Q = P + rng.normal(size=(n, 3)) * 2
+        hyps = np.tile(np.eye(4), (nh, 1, 1))
+        hyps[:, :3, 3] = rng.normal(size=(nh, 3))
+        want = O.score_hypotheses_3d(hyps, P, Q)
+        got = ops.ransac3d_score(torch.from_numpy(hyps).cuda(), ops.pack_xyzw(torch.from_numpy(P).cuda()),
+                                 ops.pack_xyzw(torch.from_numpy(Q).cuda())).cpu().numpy()
+        assert np.array_equal(got, want), (n, nh)

@@ -1,0 +1,85 @@
+"""CPU-only host logic: shard partition, all-gather of transforms over gloo (world_size 2 and 3),
+chaining, drop-in argument handling that never reaches the device."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, sub
+from oracle import ref_port as O
+
+
+def test_shard_range_partitions_exactly():
+    pipeline = sub("pipeline")
+    for n in (0, 1, 7, 8, 1024, 1031):
+        for world in (1, 2, 3, 8):
+            spans = [pipeline.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_total, out_dir):
+    sys.path.insert(0, ROOT)
+    import importlib
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
+    rng = np.random.default_rng(123)
+    all_T = rng.normal(size=(n_total, 4, 4))           # every rank can regenerate the global truth
+    s, e = pipeline.shard_range(n_total, rank, world)
+    local = torch.from_numpy(all_T[s:e].copy())
+    gathered = pipeline.gather_transforms(local, n_total)
+    ok = np.array_equal(gathered.numpy(), all_T)
+    chained = pipeline.chain(gathered)
+    ok = ok and np.array_equal(chained, np.stack(O.chain_prefix(list(all_T))))
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 10), (2, 7), (3, 8)])
+def test_gather_transforms_gloo(tmp_path, world, n_total):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def test_drop_in_argument_errors_do_not_need_a_gpu():
+    r3d = sub("utils.r3d")
+    A = np.zeros((5, 3))
+    with pytest.raises(Exception) as ei:
+        r3d.rigid_transform_3D(A, A)
+    assert "not 3xN" in str(ei.value)
+    with pytest.raises(AssertionError):
+        r3d.rigid_transform_3D(np.zeros((3, 5)), np.zeros((2, 5)))
+    q9 = sub("utils.homography_utils.q9")
+    with pytest.raises(IndexError):
+        q9.make_binned_array((10, 10), np.array([[50.0, 2.0]]))
+    with pytest.raises(NotImplementedError):
+        sub("utils.utils").depth_to_voxel(np.zeros((4, 4), np.uint16), scale=2)
+
+
+def test_q9_host_side_dlt_matches_oracle():
+    q9 = sub("utils.homography_utils.q9")
+    rng = np.random.default_rng(5)
+    ms = [q9.Match(*rng.uniform(0, 100, 4)) for _ in range(6)]
+    A = q9.make_homography_LS_matrix(ms)
+    assert np.array_equal(A, O.dlt_design([O.Match(*m) for m in ms]))
+    assert np.array_equal(q9.solve_homography_LS_matrix(A), O.dlt_solve(A))
