@@ -22,6 +22,7 @@
 namespace r3d {
 
 constexpr int NN_THREADS = 128;
+constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent nn kernel (see nn_kernel)
 
 struct PairState {
     double T[12];        // cumulative transform, rows 0..2 of the 4x4
@@ -54,6 +55,7 @@ struct IcpWorkspace {
     int grp_cap;
     int* n_grp;            // [pair]
     int nn_ctas;           // CTAs per pair of the persistent nn kernel
+    int* vw_counter;       // [pair] next virtual warp of the running nn launch (reset by its consumer)
     int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
     double* d2;            // [pair][max_src]
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
@@ -67,6 +69,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
     w.src_rows = w.src_tiles * (NN_THREADS / 32);
+    if (w.src_rows < NN_VWARPS) w.src_rows = NN_VWARPS;
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
     w.src_desc = a.take<SortDesc>(P);
@@ -85,12 +88,14 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.grp_cap = max_src + 1;
     w.grp = a.take<uint32_t>(P * (size_t)w.grp_cap);
     w.n_grp = a.take<int>(P);
+    w.vw_counter = a.take<int>(P);
     {
         // persistent nn kernel: enough CTAs to fill 148 SMs x 8 resident CTAs over the chunk's pairs,
         // never more than one warp per 32 queries
         int per_pair = (148 * 8 + n_pairs - 1) / n_pairs;
         const int cap = (max_src + NN_THREADS - 1) / NN_THREADS;
         if (per_pair > cap) per_pair = cap;
+        if (per_pair > NN_VWARPS / (NN_THREADS / 32)) per_pair = NN_VWARPS / (NN_THREADS / 32);
         if (per_pair < 1) per_pair = 1;
         w.nn_ctas = per_pair;
     }
@@ -119,6 +124,7 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     s.pad = 0;
     if (s.n_src <= 0 || w.grid.params[pair].n_pts <= 0) s.done = 1;
     w.state[pair] = s;
+    w.vw_counter[pair] = 0;
     w.src_desc[pair].n = s.n_src > 0 ? s.n_src : 0;
     w.src_desc[pair].n_passes = w.grid.params[pair].n_passes;
 }
@@ -408,9 +414,19 @@ nn_kernel(IcpWorkspace w, int write_d2) {
     int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
     const int n_tasks = (s_ngrp + NGW - 1) / NGW;
-    double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this warp's tasks
-
-    for (int task = blockIdx.x * (NN_THREADS / 32) + warp; task < n_tasks; task += gridDim.x * (NN_THREADS / 32)) {
+    // Work is dealt to NN_VWARPS "virtual warps" per pair (virtual warp u owns tasks u, u + NN_VWARPS, ...)
+    // and each physical warp runs some of them back to back.  The moment sums are kept per VIRTUAL warp,
+    // so their summation order -- and therefore every bit of the result -- does not depend on how many
+    // CTAs this launch happened to get (chunk size, number of pairs in flight, GPU count).
+    // virtual warps are handed out dynamically (which physical warp runs one does not matter)
+    int* vw_counter = w.vw_counter + pair;
+    while (true) {
+    int vw = 0;
+    if (lane == 0) vw = atomicAdd(vw_counter, 1);
+    vw = __shfl_sync(0xffffffffu, vw, 0);
+    if (vw >= NN_VWARPS) break;
+    double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
+    for (int task = vw; task < n_tasks; task += NN_VWARPS) {
         const int gid = task * NGW + lane / G;
         bool active = false;
         int i = 0;
@@ -451,9 +467,9 @@ nn_kernel(IcpWorkspace w, int write_d2) {
             acc += warp_reduce16(m, reinterpret_cast<double*>(stage[warp]));
         }
     }
-    // every warp of the grid writes its row (zeros if it had no task): solve_kernel sums them all
-    if (FUSED && lane < 16)
-        w.partial[((size_t)pair * w.src_rows + (size_t)(blockIdx.x * (NN_THREADS / 32) + warp)) * 16 + lane] = acc;
+    // every virtual warp writes its row (zeros if it had no task): solve_kernel sums NN_VWARPS rows
+    if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
+    }
 }
 
 // ---- partial-set selection ---------------------------------------------------------------------------
@@ -618,6 +634,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     const int pair = blockIdx.x;
     PairState* st = w.state + pair;
+    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
     if (st->done) return;
     __shared__ double sm[SOLVE_THREADS];
     __shared__ double m[16];
@@ -841,7 +858,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
             R3D_LAUNCH(select_kernel, P, 1024, 0, st, w);
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
         }
-        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? w.nn_ctas * (NN_THREADS / 32) : 0);
+        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? NN_VWARPS : 0);
     }
     R3D_LAUNCH(final_kernel, (P + 63) / 64, 64, 0, st, w, T_out, iters_out, mean_err_out);
     if ((last_idx || last_dist || last_keep) && prm.max_iterations > 0) {

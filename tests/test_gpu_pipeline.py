@@ -42,7 +42,9 @@ def test_device_and_host_paths_agree_with_drop_ins():
         assert np.array_equal(T, Td[p]), "batched and single-pair paths must be bitwise identical"
         Tr, _, itr = O.icp(A, B, max_iterations=8, tolerance=0.0)
         assert it == itr == int(host["iters"][p])
-        assert_transform_parity(Td[p], Tr, O.scene_extent(B), "pair %d" % p, 1e-6, 1e-7)
+        # vs the KD-tree oracle: exact distance ties on quantised depth resolve differently, so the
+        # north_star tolerance applies (1e-4), not bitwise equality
+        assert_transform_parity(Td[p], Tr, O.scene_extent(B), "pair %d" % p)
     assert host["n_src"][3] == 0
 
 
