@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libr3d_b200.so")
+# R3D_LIB_PATH selects another build of the same library (tools/ use the diagnostic twin built with R3D_NN_STATS=1)
+LIB_PATH = os.environ.get("R3D_LIB_PATH") or os.path.join(_HERE, "lib", "libr3d_b200.so")
 
 c_void_p, c_int, c_size_t, c_double, c_int64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_double,
                                                 ctypes.c_int64)
@@ -64,6 +65,7 @@ SIGNATURES = {
     "r3d_launch_count": (ctypes.c_uint64, []),
     "r3d_nn_timing_enable": (None, [c_int]),
     "r3d_nn_timing_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int]),
+    "r3d_nn_stats_read": (c_int, [ctypes.POINTER(ctypes.c_uint64), c_int]),
 }
 
 _lib = None

@@ -14,8 +14,12 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
-LIB = os.path.join(LIBDIR, "libr3d_b200.so")
+# R3D_NN_STATS=1 builds a diagnostic twin (search counters compiled in) next to the product library
+# R3D_BUILD_TAG=<tag> (with any of the R3D_* compile-time knobs) builds an experimental twin for tools/ sweeps
+_STATS = bool(os.environ.get("R3D_NN_STATS"))
+_TAG = os.environ.get("R3D_BUILD_TAG") or ("stats" if _STATS else "")
+OBJDIR = os.path.join(HERE, "build_" + _TAG if _TAG else "build")
+LIB = os.path.join(LIBDIR, "libr3d_b200_%s.so" % _TAG if _TAG else "libr3d_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC_FLAGS = [
@@ -23,7 +27,9 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-] + (["-DR3D_NN_MIN_CTAS=" + os.environ["R3D_NN_MIN_CTAS"]] if os.environ.get("R3D_NN_MIN_CTAS") else [])
+] + (["-DR3D_NN_MIN_CTAS=" + os.environ["R3D_NN_MIN_CTAS"]] if os.environ.get("R3D_NN_MIN_CTAS") else []) \
+  + (["-DR3D_LEAN_MIN_CTAS=" + os.environ["R3D_LEAN_MIN_CTAS"]] if os.environ.get("R3D_LEAN_MIN_CTAS") else []) \
+  + (["-DR3D_NN_STATS"] if os.environ.get("R3D_NN_STATS") else [])
 
 
 def _nvcc():

@@ -14,7 +14,7 @@
 //                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126)
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
-#include "coop_search.cuh"
+#include "lean_search.cuh"
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -156,7 +156,20 @@ src_keys_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t* _
     const int ix = cell_coord((qx - g.ox) * g.inv_cell, g.nx);
     const int iy = cell_coord((qy - g.oy) * g.inv_cell, g.ny);
     const int iz = cell_coord((qz - g.oz) * g.inv_cell, g.nz);
-    const uint32_t blk = (uint32_t)(((iz >> 2) * g.by + (iy >> 2)) * g.bx + (ix >> 2));
+    // Block order of the QUERY sort: the axis with the fewest blocks runs fastest.  A depth-image cloud
+    // is a height field over its two long axes, so stepping along a long axis moves to a block that
+    // touches the previous one; with the destination grid's own x-fastest order a run of consecutive
+    // queries would keep jumping between far-apart blocks of one block row.
+    const int cb[3] = {ix >> 2, iy >> 2, iz >> 2};
+    const int nb[3] = {g.bx, g.by, g.bz};
+    int o0 = 0, o1 = 1, o2 = 2;      // o0 fastest ... o2 slowest
+    if (nb[o1] < nb[o0]) { const int t = o0; o0 = o1; o1 = t; }
+    if (nb[o2] < nb[o0]) { const int t = o0; o0 = o2; o2 = t; }
+    if (nb[o2] < nb[o1]) { const int t = o1; o1 = o2; o2 = t; }
+    const int c0 = (o0 == 0) ? cb[0] : (o0 == 1) ? cb[1] : cb[2], n0 = (o0 == 0) ? nb[0] : (o0 == 1) ? nb[1] : nb[2];
+    const int c1 = (o1 == 0) ? cb[0] : (o1 == 1) ? cb[1] : cb[2], n1 = (o1 == 0) ? nb[0] : (o1 == 1) ? nb[1] : nb[2];
+    const int c2 = (o2 == 0) ? cb[0] : (o2 == 1) ? cb[1] : cb[2];
+    const uint32_t blk = (uint32_t)((c2 * n1 + c1) * n0 + c0);
     const uint32_t fine = (uint32_t)((((iz >> 1) & 1) << 5) | (((iy >> 1) & 1) << 4) | (((ix >> 1) & 1) << 3) |
                                      ((iz & 1) << 2) | ((iy & 1) << 1) | (ix & 1));
     w.skeys[0][(size_t)pair * w.max_src + i] = (blk << 6) | fine;
@@ -390,6 +403,11 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
 #ifndef R3D_NN_MIN_CTAS
 #define R3D_NN_MIN_CTAS 4
 #endif
+// the lean kernel is latency bound: 8 CTAs x 4 warps per SM (64 registers, a few bytes of spill) measured
+// 13% faster than 4 (profiles/r01_nn_sweeps.md)
+#ifndef R3D_LEAN_MIN_CTAS
+#define R3D_LEAN_MIN_CTAS 8
+#endif
 template <int G, bool SEEDED, bool FUSED>
 __global__ void __launch_bounds__(NN_THREADS, R3D_NN_MIN_CTAS)
 nn_kernel(IcpWorkspace w, int write_d2) {
@@ -469,6 +487,77 @@ nn_kernel(IcpWorkspace w, int write_d2) {
     }
     // every virtual warp writes its row (zeros if it had no task): solve_kernel sums NN_VWARPS rows
     if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
+    }
+}
+
+// Lean variant (lean_search.cuh): a task is 32 consecutive queries of the sorted source cloud; no
+// group table.  Same virtual-warp scheme, so the moment sums are independent of the launch geometry.
+template <bool SEEDED, bool FUSED>
+__global__ void __launch_bounds__(NN_THREADS, R3D_LEAN_MIN_CTAS)
+nn_lean_kernel(IcpWorkspace w, int write_d2) {
+    const int pair = blockIdx.y;
+    __shared__ GridParams g;
+    __shared__ double T[12];
+    __shared__ int s_n, s_done;
+    __shared__ __align__(16) double scratch[NN_THREADS / 32][16 * 33];     // moment reduction scratch
+    // survivors list of each warp; never shared with the reduction: its stale slots must stay real points
+    __shared__ double2 lists[NN_THREADS / 32][2 * LEAN_LIST_CAP];
+    if (threadIdx.x == 0) {
+        g = w.grid.params[pair];
+        s_n = w.state[pair].n_src;
+        s_done = w.state[pair].done;
+    }
+    if (threadIdx.x < 12) T[threadIdx.x] = w.state[pair].T[threadIdx.x];
+    __syncthreads();
+    if (s_done) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GridView v = grid_view(w.grid, pair);
+    const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
+    int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
+    double* d2_out = w.d2 + (size_t)pair * w.max_src;
+    const int n_tasks = (s_n + 31) >> 5;
+    int* vw_counter = w.vw_counter + pair;
+    list_init(lists[warp], v.pts);
+    while (true) {
+        int vw = 0;
+        if (lane == 0) vw = atomicAdd(vw_counter, 1);
+        vw = __shfl_sync(0xffffffffu, vw, 0);
+        if (vw >= NN_VWARPS) break;
+        double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
+        for (int task = vw; task < n_tasks; task += NN_VWARPS) {
+            const int i = task * 32 + lane;
+            const bool active = i < s_n;
+            double qx = 0.0, qy = 0.0, qz = 0.0;
+            Best best;
+            best.d2 = CUDART_INF;
+            best.idx = 0x7fffffff;
+            best.pos = -1;      // no seed: no sorted position to exclude from the scan
+            if (active) {
+                const Point4 a = load_point(src + i);
+                qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
+                qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
+                qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
+                if (SEEDED) consider(best, v.pts, nn_pos[i], qx, qy, qz);
+            }
+            R3D_STAT(0, 1);
+            lean_search(lists[warp], best, v, g, active, qx, qy, qz);
+            if (active) {
+                nn_pos[i] = best.pos;
+                if (!FUSED || write_d2) d2_out[i] = best.d2;
+            }
+            if (FUSED) {
+                double m[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) m[k] = 0.0;
+                if (active) {
+                    const Point4 b = load_point(v.pts + best.pos);
+                    accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
+                                    b.z - g.shift[2], sqrt(best.d2));
+                }
+                acc += warp_reduce16(m, scratch[warp]);
+            }
+        }
+        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
     }
 }
 
@@ -810,7 +899,21 @@ static int launch_nn_g(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int 
     return R3D_OK;
 }
 
+static std::atomic<int> g_nn_impl{1};      // 1 = lean walk (lean_search.cuh), 0 = staged lists (coop_search.cuh)
+
+static int launch_lean(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+    if (seeded) {
+        if (fused) R3D_LAUNCH((nn_lean_kernel<true, true>), grid, NN_THREADS, 0, st, w, write_d2);
+        else R3D_LAUNCH((nn_lean_kernel<true, false>), grid, NN_THREADS, 0, st, w, write_d2);
+    } else {
+        if (fused) R3D_LAUNCH((nn_lean_kernel<false, true>), grid, NN_THREADS, 0, st, w, write_d2);
+        else R3D_LAUNCH((nn_lean_kernel<false, false>), grid, NN_THREADS, 0, st, w, write_d2);
+    }
+    return R3D_OK;
+}
+
 static int launch_nn(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+    if (g_nn_impl.load() == 1) return launch_lean(w, grid, seeded, fused, write_d2, st);
     switch (g_group_size.load()) {
         case 32: return launch_nn_g<32>(w, grid, seeded, fused, write_d2, st);
         case 16: return launch_nn_g<16>(w, grid, seeded, fused, write_d2, st);
@@ -824,6 +927,7 @@ static int sort_source(IcpWorkspace& w, const Point4* src, const int32_t* src_of
     int rc = radix_sort_pairs(w.skeys, w.svals, w.shist, w.src_desc, w.n_pairs, w.max_src, w.src_rtiles, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(src_gather_kernel, g256, 256, 0, st, w, src, src_off);
+    if (g_nn_impl.load() == 1) return R3D_OK;      // the lean walk takes 32 consecutive queries per task
     // query groups (never straddling a block)
     const dim3 gseg(w.seg_tiles, w.n_pairs);
     R3D_LAUNCH(seg_count_kernel, gseg, 256, 0, st, w);
@@ -962,12 +1066,36 @@ extern "C" int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* 
     return R3D_OK;
 }
 
+extern "C" int r3d_nn_stats_read(uint64_t* out8_host, int reset) {
+#ifdef R3D_NN_STATS
+    if (out8_host) {
+        cudaError_t e = cudaMemcpyFromSymbol(out8_host, g_nn_stats, 8 * sizeof(unsigned long long));
+        if (e != cudaSuccess) { set_cuda_error(e, "nn stats"); return R3D_ERR_CUDA; }
+    }
+    if (reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaError_t e = cudaMemcpyToSymbol(g_nn_stats, z, sizeof(z));
+        if (e != cudaSuccess) { set_cuda_error(e, "nn stats"); return R3D_ERR_CUDA; }
+    }
+    return R3D_OK;
+#else
+    (void)out8_host; (void)reset;
+    return R3D_ERR_INVALID;      // the library was built without -DR3D_NN_STATS
+#endif
+}
+
 extern "C" int r3d_set_option(int option, double value) {
     switch (option) {
         case R3D_OPT_GROUP_SIZE: {
             const int gsz = (int)value;
             if (gsz != 8 && gsz != 16 && gsz != 32) return R3D_ERR_INVALID;
             g_group_size.store(gsz);
+            return R3D_OK;
+        }
+        case R3D_OPT_NN_IMPL: {
+            const int impl = (int)value;
+            if (impl != 0 && impl != 1) return R3D_ERR_INVALID;
+            g_nn_impl.store(impl);
             return R3D_OK;
         }
         case R3D_OPT_CELL_FACTOR:

@@ -1,0 +1,296 @@
+// Warp-union exact nearest-neighbour search on the sparse-block grid.
+//
+// Same contract as coop_search.cuh (exact NN, lowest-index tie-break, equal to float64 brute
+// force; utils/icp.py:58-71 up to exact ties).  A warp owns 32 consecutive queries of the
+// spatially sorted source cloud, shares ONE candidate stream, and every lane evaluates every
+// candidate that survives a box filter:
+//   1. every lane turns its upper bound into a ball and the ball into a box of cells; the warp
+//      takes the union box (REDUX min/max) and the union of the balls' bounding boxes in world
+//      coordinates (the filter box);
+//   2. the (y,z) rows of the union box, cut at block borders, are the warp's segments: 32 of them
+//      are looked up at a time, one per lane (one hash probe + two cell-start loads), and each lane
+//      keeps the sorted-cloud range [s, s+cnt) of its segment in registers;
+//   3. the concatenation of the segments is the candidate stream.  Per batch of 32 stream indices
+//      every lane resolves one index to a sorted position (binary search over the warp's prefix
+//      sums, by SHFL) and loads THAT point: consecutive lanes read consecutive 32-byte records
+//      (coalesced, 32 independent loads in flight) and the next batch's loads are issued before
+//      the current one is consumed.  Points outside the filter box are dropped (they are outside
+//      every lane's ball); the survivors are ballot-compacted into a small per-warp shared-memory
+//      list;
+//   4. when the list holds enough points every lane scans it by broadcast LDS and keeps the
+//      lexicographic minimum of (squared distance, cloud index) in fp64.
+// A lane may evaluate points it did not need (they are real points of the cloud, so any of them
+// is a valid bound), which is why nothing in the scan is predicated per lane.
+// Boxes with more than LEAN_SEG_CAP segments (far outliers, queries far outside the cloud) fall
+// back to the per-lane bounded search of grid.cuh, which has the block-list mode.
+#pragma once
+#include "coop_search.cuh"
+
+namespace r3d {
+
+constexpr int LEAN_SEG_CAP = 2048;     // segments per round the warp walk accepts
+constexpr int LEAN_LIST_CAP = 64;      // survivors list: at most LEAN_FLUSH - 1 + 32 entries between flushes
+constexpr int LEAN_FLUSH = 24;         // scan the list as soon as it holds this many points
+#ifndef R3D_FULL_MASK_DEFINED
+#define R3D_FULL_MASK_DEFINED
+constexpr unsigned FULL = 0xffffffffu;
+#endif
+
+// Diagnostic counters (builds with -DR3D_NN_STATS only; read by r3d_nn_stats_read):
+//   0 tasks  1 search rounds  2 candidate evaluations per lane  3 rounds with per-lane fallback
+//   4 segment lookup rounds   5 segments looked up              6 non-empty segments
+//   7 candidates loaded (before the box filter)
+#ifdef R3D_NN_STATS
+static __device__ unsigned long long g_nn_stats[8];      // this header is included by icp.cu only
+#define R3D_STAT(slot, n)                                                                   \
+    do {                                                                                    \
+        const unsigned long long _v = (unsigned long long)(n); /* evaluated by every lane */ \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_nn_stats[slot], _v);                      \
+    } while (0)
+#else
+#define R3D_STAT(slot, n) do { } while (0)
+#endif
+
+// one candidate of the list: xy = (x, y), zw = (z, cloud index | sorted position << 32)
+// (ptxas turns the update into predicated moves whatever the source says -- a vote-guarded branch was
+// measured slower, profiles/r01_nn_sweeps.md -- so the test is kept minimal)
+__device__ __forceinline__ void eval_staged(Best& best, const double2 xy, const double2 zw, double qx, double qy, double qz) {
+    const double dx = qx - xy.x, dy = qy - xy.y, dz = qz - zw.x;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    const int idx = __double2loint(zw.y);
+    if (d2 < best.d2 || (d2 == best.d2 && idx < best.idx)) {
+        best.d2 = d2;
+        best.idx = idx;
+        best.pos = __double2hiint(zw.y);
+    }
+}
+
+struct WarpList {
+    double2* sxy;      // [LEAN_LIST_CAP] (x, y)
+    double2* szw;      // [LEAN_LIST_CAP] (z, tag)
+    int n;             // warp-uniform
+    double lo[3], hi[3];      // filter box (world coordinates)
+};
+
+// Every lane scans the list, four entries at a time.  Slots past n hold points of earlier batches (or
+// the point the list was initialised with): real points of the same cloud, harmless to re-evaluate.
+__device__ __forceinline__ void list_flush(WarpList& L, Best& best, double qx, double qy, double qz) {
+    __syncwarp();
+    const int n = L.n;
+    R3D_STAT(2, (n + 3) & ~3);
+#pragma unroll 1
+    for (int u = 0; u < n; u += 4) {
+        const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + 1], b1 = L.szw[u + 1];
+        const double2 a2 = L.sxy[u + 2], b2 = L.szw[u + 2], a3 = L.sxy[u + 3], b3 = L.szw[u + 3];
+        eval_staged(best, a0, b0, qx, qy, qz);
+        eval_staged(best, a1, b1, qx, qy, qz);
+        eval_staged(best, a2, b2, qx, qy, qz);
+        eval_staged(best, a3, b3, qx, qy, qz);
+    }
+    __syncwarp();
+    L.n = 0;
+}
+
+// Fill every slot of a warp's list with a real point of the cloud (once per kernel and pair).
+__device__ __forceinline__ void list_init(double2* list, const Point4* __restrict__ pts) {
+    const int lane = threadIdx.x & 31;
+    const double2* p = reinterpret_cast<const double2*>(pts);
+    const double2 xy = __ldg(p);
+    double2 zw = __ldg(p + 1);
+    zw.y = __hiloint2double(0, __double2loint(zw.y));
+#pragma unroll
+    for (int k = lane; k < LEAN_LIST_CAP; k += 32) {
+        list[k] = xy;
+        list[LEAN_LIST_CAP + k] = zw;
+    }
+    __syncwarp();
+}
+
+// Walk every cell of the warp's box [lo, hi] (warp-uniform ints, at most LEAN_SEG_CAP segments).
+__device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, const GridView& v, const GridParams& g, int lox, int loy,
+                                              int loz, int hix, int hiy, int hiz, double qx, double qy, double qz) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int ny = hiy - loy + 1, nz = hiz - loz + 1;
+    const int bx0 = lox >> 2, bx1 = hix >> 2;
+    const int nxb = bx1 - bx0 + 1;
+    const int nseg = ny * nz * nxb;
+    // exact for the small integers involved (nseg <= LEAN_SEG_CAP): quotient by reciprocal, then fix up
+    const float inv_nxb = 1.0f / (float)nxb, inv_ny = 1.0f / (float)ny;
+    R3D_STAT(5, nseg);
+    for (int base = 0; base < nseg; base += 32) {
+        R3D_STAT(4, 1);
+        const int sidx = base + lane;
+        uint32_t s = 0, cnt = 0;
+        if (sidx < nseg) {
+            int row = (int)((float)sidx * inv_nxb);
+            row += (sidx - row * nxb >= nxb) - (sidx - row * nxb < 0);
+            const int j = sidx - row * nxb;
+            int rz = (int)((float)row * inv_ny);
+            rz += (row - rz * ny >= ny) - (row - rz * ny < 0);
+            const int iy = loy + (row - rz * ny), iz = loz + rz;
+            const int cbx = bx0 + j, cby = iy >> 2, cbz = iz >> 2;
+            const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
+            const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
+            if (b >= 0) {
+                const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
+                const uint32_t* cs = v.cell_start + (size_t)b * 64 + (((iz & 3) << 4) | ((iy & 3) << 2));
+                s = __ldg(cs + x0);
+                cnt = __ldg(cs + x1 + 1) - s;
+            }
+        }
+        // candidate stream = concatenation of the 32 segments; stream index t lives in the segment j
+        // with excl_j <= t < excl_j + cnt_j (exclusive prefix sums of cnt)
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t excl = incl - cnt;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        R3D_STAT(6, __popc(__ballot_sync(FULL, cnt > 0)));
+        R3D_STAT(7, total);
+        if (total == 0u) continue;
+        double2 xy = make_double2(0.0, 0.0), zw = make_double2(0.0, 0.0);
+        bool have = false;
+        // resolve stream index t = t0 + lane and issue its loads
+        auto fetch = [&](uint32_t t0) {
+            const uint32_t t = t0 + (uint32_t)lane;
+            have = t < total;
+            const uint32_t tc = min(t, total - 1u);
+            int seg = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t ex = __shfl_sync(FULL, excl, seg + step);
+                if (ex <= tc) seg += step;
+            }
+            const uint32_t pos = __shfl_sync(FULL, s, seg) + (tc - __shfl_sync(FULL, excl, seg));
+            if (have) {
+                const double2* p = reinterpret_cast<const double2*>(v.pts + pos);
+                xy = __ldg(p);
+                zw = __ldg(p + 1);
+                zw.y = __hiloint2double((int)pos, __double2loint(zw.y));
+            }
+        };
+        fetch(0u);
+        for (uint32_t t0 = 0; t0 < total; t0 += 32) {
+            const bool keep = have && xy.x >= L.lo[0] && xy.x <= L.hi[0] && xy.y >= L.lo[1] && xy.y <= L.hi[1] &&
+                              zw.x >= L.lo[2] && zw.x <= L.hi[2];
+            const unsigned bal = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int slot = L.n + __popc(bal & lt);
+                L.sxy[slot] = xy;
+                L.szw[slot] = zw;
+            }
+            L.n += __popc(bal);
+            if (t0 + 32 < total) fetch(t0 + 32);          // next batch's loads fly while the list is scanned
+            if (L.n >= LEAN_FLUSH) list_flush(L, best, qx, qy, qz);
+        }
+    }
+    if (L.n > 0) list_flush(L, best, qx, qy, qz);
+}
+
+// Exact NN for the warp's 32 queries.  `best` holds a valid upper bound (a real point of the cloud)
+// for lanes that have one, d2 = +inf otherwise.  Inactive lanes take part in the collectives only.
+// `list`: 2 * LEAN_LIST_CAP double2 of shared memory owned by the warp.
+//
+// Expanding search in rounds.  Every unfinished lane asks for the ball of radius min(its bound, its
+// rcap), i.e. a box of cells.  Consecutive queries are usually neighbours in space, but a run of 32
+// can straddle two blocks that are far apart (a surface leaves and re-enters a row of blocks), so a
+// round serves the lanes around a LEADER (the first unfinished lane): those whose box lies inside a
+// window around the leader's.  The union box of the served lanes is walked; a served lane is
+// finished once its best distance is within the radius it asked for (nothing unseen can be closer),
+// otherwise its rcap doubles.  Lanes left out wait for a later round with a leader near them.  Lanes
+// that arrive with a bound (the previous iteration's neighbour) ask for their full ball at once, so a
+// coherent warp takes one round.
+constexpr int LEAN_WIN = 4;      // served: box inside the leader's box widened by max(4 cells, its own extent)
+
+// float -> int map that preserves order under SIGNED comparison (and is its own inverse)
+__device__ __forceinline__ int f2sord(float f) {
+    const int b = __float_as_int(f);
+    return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float sord2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
+__device__ __forceinline__ float wmin_f(float v) { return sord2f(__reduce_min_sync(0xffffffffu, f2sord(v))); }
+__device__ __forceinline__ float wmax_f(float v) { return sord2f(__reduce_max_sync(0xffffffffu, f2sord(v))); }
+// cell index of a float cell coordinate, clamped into [0, n-1] (NaN -> 0)
+__device__ __forceinline__ int cell_lo(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
+__device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
+
+__device__ __forceinline__ void lean_search(double2* list, Best& best, const GridView& v, const GridParams& g, bool active,
+                                            double qx, double qy, double qz) {
+    // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
+    // margin: 2e-3 cells absolute plus 2.4e-7 relative to the coordinate (one float ulp), on top of the
+    // 1e-6 relative slack of the radius.
+    const float tqx = (float)((qx - g.ox) * g.inv_cell), tqy = (float)((qy - g.oy) * g.inv_cell),
+                tqz = (float)((qz - g.oz) * g.inv_cell);
+    const float mgx = fmaf(fabsf(tqx), 2.4e-7f, 2e-3f), mgy = fmaf(fabsf(tqy), 2.4e-7f, 2e-3f),
+                mgz = fmaf(fabsf(tqz), 2.4e-7f, 2e-3f);
+    const float inv_cell = (float)g.inv_cell * 1.000001f;
+    const float qxf_lo = __double2float_rd(qx), qxf_hi = __double2float_ru(qx);
+    const float qyf_lo = __double2float_rd(qy), qyf_hi = __double2float_ru(qy);
+    const float qzf_lo = __double2float_rd(qz), qzf_hi = __double2float_ru(qz);
+    const int big = 0x7fffffff;
+    const float inf = __int_as_float(0x7f800000);
+    WarpList L;
+    L.sxy = list;
+    L.szw = list + LEAN_LIST_CAP;
+    L.n = 0;
+    float rcap = (best.d2 < CUDART_INF) ? inf : (float)g.cell;
+    bool fin = !active;
+    while (true) {
+        const unsigned unfin = __ballot_sync(FULL, !fin);
+        if (unfin == 0u) return;
+        R3D_STAT(1, 1);
+        const int leader = __ffs(unfin) - 1;
+        // float sqrt rounded up
+        const float rl = sqrtf((float)best.d2) * 1.000001f + 1e-30f;
+        const float ruse = fminf(rl, rcap);
+        const float rc = ruse * inv_cell;
+        const int mlox = cell_lo(tqx - rc - mgx, g.nx), mhix = cell_hi(tqx + rc + mgx, g.nx);
+        const int mloy = cell_lo(tqy - rc - mgy, g.ny), mhiy = cell_hi(tqy + rc + mgy, g.ny);
+        const int mloz = cell_lo(tqz - rc - mgz, g.nz), mhiz = cell_hi(tqz + rc + mgz, g.nz);
+        // window around the leader's box (always contains the leader's own box)
+        const int Llox = __shfl_sync(FULL, mlox, leader), Lhix = __shfl_sync(FULL, mhix, leader);
+        const int Lloy = __shfl_sync(FULL, mloy, leader), Lhiy = __shfl_sync(FULL, mhiy, leader);
+        const int Lloz = __shfl_sync(FULL, mloz, leader), Lhiz = __shfl_sync(FULL, mhiz, leader);
+        const int wx = max(LEAN_WIN, Lhix - Llox + 1), wy = max(LEAN_WIN, Lhiy - Lloy + 1), wz = max(LEAN_WIN, Lhiz - Lloz + 1);
+        const bool part = !fin && mlox >= Llox - wx && mhix <= Lhix + wx && mloy >= Lloy - wy && mhiy <= Lhiy + wy &&
+                          mloz >= Lloz - wz && mhiz <= Lhiz + wz;
+        const int lox = __reduce_min_sync(FULL, part ? mlox : big), hix = __reduce_max_sync(FULL, part ? mhix : -1);
+        const int loy = __reduce_min_sync(FULL, part ? mloy : big), hiy = __reduce_max_sync(FULL, part ? mhiy : -1);
+        const int loz = __reduce_min_sync(FULL, part ? mloz : big), hiz = __reduce_max_sync(FULL, part ? mhiz : -1);
+        const bool whole = lox == 0 && loy == 0 && loz == 0 && hix == g.nx - 1 && hiy == g.ny - 1 && hiz == g.nz - 1;
+        const long long nseg = (long long)(hiy - loy + 1) * (hiz - loz + 1) * ((hix >> 2) - (lox >> 2) + 1);
+        if (nseg <= (long long)LEAN_SEG_CAP) {
+            // the union of the served balls' bounding boxes in world coordinates: a point outside it is
+            // outside every served ball.  When the box is the whole grid everything is looked at once and
+            // the answer is final for every lane, so nothing may be filtered.
+            const float rw = ruse * 1.000001f;
+            const float l0 = wmin_f(part ? __fsub_rd(qxf_lo, rw) : inf), h0 = wmax_f(part ? __fadd_ru(qxf_hi, rw) : -inf);
+            const float l1 = wmin_f(part ? __fsub_rd(qyf_lo, rw) : inf), h1 = wmax_f(part ? __fadd_ru(qyf_hi, rw) : -inf);
+            const float l2 = wmin_f(part ? __fsub_rd(qzf_lo, rw) : inf), h2 = wmax_f(part ? __fadd_ru(qzf_hi, rw) : -inf);
+            L.lo[0] = whole ? -CUDART_INF : (double)l0; L.hi[0] = whole ? CUDART_INF : (double)h0;
+            L.lo[1] = whole ? -CUDART_INF : (double)l1; L.hi[1] = whole ? CUDART_INF : (double)h1;
+            L.lo[2] = whole ? -CUDART_INF : (double)l2; L.hi[2] = whole ? CUDART_INF : (double)h2;
+            lean_scan_box(L, best, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
+            if (part) {
+                const float rn = sqrtf((float)best.d2) * 1.000001f + 1e-30f;
+                fin = whole || (rn <= ruse) || !(ruse < 1e37f);
+                rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the union) must not set the next radius
+            }
+        } else {
+            R3D_STAT(3, 1);
+            if (part) {
+                // far outliers / queries far outside the cloud: per-lane exact search with the block-list mode
+                if (!(best.d2 < CUDART_INF)) seed_search(best, v, g, qx, qy, qz);
+                bounded_search(best, v, g, qx, qy, qz);
+                fin = true;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace r3d

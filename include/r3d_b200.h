@@ -202,8 +202,9 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
 
 /* Tuning knobs; none of them changes results.  R3D_OPT_GROUP_SIZE: lanes that share one staged
  * candidate list in the NN search (8, 16 or 32).  R3D_OPT_CELL_FACTOR: automatic grid cell edge in
- * units of the estimated point spacing (used when cell_size <= 0). */
-typedef enum { R3D_OPT_GROUP_SIZE = 1, R3D_OPT_CELL_FACTOR = 2 } r3d_option;
+ * units of the estimated point spacing (used when cell_size <= 0).  R3D_OPT_NN_IMPL: 1 = lean
+ * group-union walk (default), 0 = staged candidate lists. */
+typedef enum { R3D_OPT_GROUP_SIZE = 1, R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3 } r3d_option;
 int r3d_set_option(int option, double value);
 
 /* Number of kernels this library has launched since load (all entry points). */
@@ -215,6 +216,12 @@ uint64_t r3d_launch_count(void);
  * queries processed since the last reset. */
 void r3d_nn_timing_enable(int on);
 int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* queries, int reset);
+
+/* Diagnostic counters of the nn search (only in builds with -DR3D_NN_STATS, otherwise returns
+ * R3D_ERR_INVALID): out8_host[0..7] = tasks (warps of 32 queries), search rounds, candidate
+ * evaluations per lane, staged rounds, segment lookup rounds, segments looked up, non-empty
+ * segments walked, reserved.  Synchronous. */
+int r3d_nn_stats_read(uint64_t* out8_host, int reset);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,66 @@
+"""Timing sweep of the nn-search variants on one chunk of synthetic pairs (device-resident inputs).
+
+    python tools/sweep_nn.py [pairs] [iters] [partial]
+
+For every (impl, group size, cell factor) it registers the same chunk twice (warm-up + timed), reads
+the library's per-launch event timing of the nn kernel, and checks that the transforms agree with
+the first configuration to 1e-9 (every variant is an exact search; only summation order may differ
+between group sizes).
+"""
+import importlib
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import ctypes  # noqa: E402
+
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+partial = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
+configs = os.environ.get("SWEEP", "0:32:2.0,1:32:2.0,1:16:2.0,1:8:2.0,1:32:1.5,1:32:1.0,1:16:1.0,1:8:1.0,1:32:3.0")
+
+pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
+C = importlib.import_module("2dto3dreconstruction_b200._capi")
+L = C.lib()
+a, b = bench.synth_batch_torch(pairs, 0, torch.device("cuda", 0))
+kw = dict(max_iterations=iters, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)
+ref = None
+for cfg in configs.split(","):
+    impl, group, factor = cfg.split(":")
+    assert L.r3d_set_option(3, float(impl)) == 0
+    assert L.r3d_set_option(1, float(group)) == 0
+    assert L.r3d_set_option(2, float(factor)) == 0
+    out = pipeline.register_depth_pairs(a, b, **kw)
+    torch.cuda.synchronize()
+    stats_on = L.r3d_nn_stats_read(None, 1) == 0      # only the diagnostic build (R3D_LIB_PATH=..._stats.so) has counters
+    L.r3d_nn_timing_enable(1)
+    t0 = time.perf_counter()
+    out = pipeline.register_depth_pairs(a, b, **kw)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ms, n, q = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+    L.r3d_nn_timing_read(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(q), 1)
+    L.r3d_nn_timing_enable(0)
+    T = out["T"].cpu()
+    if ref is None:
+        ref = T
+    dev = float((T - ref).abs().max())
+    nq = int(out["n_src"].sum())
+    print("impl %s G %2s factor %s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
+          "%.2f G corr/s in kernel | max|T - T0| %.2e err0 %.6f" % (
+              impl, group, factor, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
+              nq * n.value / max(ms.value, 1e-9) / 1e6, dev, float(out["mean_err"][0])), flush=True)
+    if stats_on:
+        st = (ctypes.c_uint64 * 8)()
+        L.r3d_nn_stats_read(st, 1)
+        tasks = max(int(st[0]), 1)
+        print("    per task of 32 queries: rounds %.2f, candidates/lane %.1f, staged rounds %.3f, lookup rounds %.2f, "
+              "segments %.1f, non-empty %.1f" % (st[1] / tasks, st[2] / tasks, st[3] / tasks, st[4] / tasks, st[5] / tasks,
+                                                 st[6] / tasks), flush=True)
+    assert dev < 1e-9, "variants disagree"
