@@ -25,7 +25,13 @@ if ROOT not in sys.path:
 
 H, W = 480, 640
 ICP_ITERS = 30
-ALGO_BYTES_PER_CORR = 40.0     # 16 src + 16 dst (amortised) + 8 idx/dist
+# 32 B source point + 32 B destination point (sorted cloud read once per launch, M ~ N)
+# + 4 B previous neighbour position read + 4 B new position written (SURVEY.md 8(d)'s 40 B is for float4 points)
+ALGO_BYTES_PER_CORR = 72.0
+# candidates evaluated per query by the warp-union walk (measured with the counter build,
+# profiles/r01_nn_sweeps.md) x 6 fp64 instructions each; FP64 pipe = 16 lanes/clk/SMSP, 592 SMSPs
+EVALS_PER_CORR = 80.0
+FP64_WARP_INSTR_PER_S = 592 * 1.965e9 / 2.0
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -39,7 +45,8 @@ def parse_args():
     ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "8")))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "2")))
     ap.add_argument("--partial", type=float, default=1.0)
-    ap.add_argument("--cpu-sample-iters", type=int, default=2)
+    ap.add_argument("--cpu-sample-iters", type=int, default=8,
+                    help="ICP iterations per pair of the bounded CPU sample (~1.3 s per iteration per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -292,12 +299,19 @@ def main():
     # rank 0's nn launches processed rank 0's correspondences
     achieved = ALGO_BYTES_PER_CORR * corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "nn_kernel (K2 exact grid NN + fused K3 moments)", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "nn_lean_kernel (K2 exact grid NN + fused K3 moments)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_correspondence": ALGO_BYTES_PER_CORR, "launches_timed": int(nn_launches.value),
         "avg_launch_ms": nn_avg_ms, "kernel_share_of_step": nn_ms.value / ms_total,
         "correspondences_per_sec_in_kernel": corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12),
     }
+    # what actually bounds the kernel: the FP64 pipe / issue slots of the candidate scan
+    fp64_instr_per_s = EVALS_PER_CORR * 6.0 / 32.0 * roofline["correspondences_per_sec_in_kernel"]
+    roofline["pipe"] = {"bound": "fp64 pipe (non-tensor)", "evaluations_per_correspondence": EVALS_PER_CORR,
+                        "achieved_fp64_warp_instr_per_s": fp64_instr_per_s, "peak_fp64_warp_instr_per_s": FP64_WARP_INSTR_PER_S,
+                        "frac": fp64_instr_per_s / FP64_WARP_INSTR_PER_S,
+                        "note": "nominal peak: 16 fp64 lanes/clk/SMSP x 592 SMSPs x 1965 MHz; evaluations per "
+                                "correspondence from the counter build (profiles/r01_nn_sweeps.md)"}
     traffic_file = os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
