@@ -26,6 +26,7 @@ constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent
 
 struct PairState {
     double T[12];        // cumulative transform, rows 0..2 of the 4x4
+    double Tp[12];       // the cumulative transform one iteration earlier (how far did every query just move?)
     double prev_err;
     double mean_err;
     double tau;          // partial mode: squared-distance threshold
@@ -57,6 +58,7 @@ struct IcpWorkspace {
     int nn_ctas;           // CTAs per pair of the persistent nn kernel
     int* vw_counter;       // [pair] next virtual warp of the running nn launch (reset by its consumer)
     int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
+    float* budget;         // [pair][max_src]  how far a query may still move before its neighbour can change (lean kernel)
     double* d2;            // [pair][max_src]
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
@@ -100,6 +102,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
         w.nn_ctas = per_pair;
     }
     w.nn_pos = a.take<int32_t>(P * max_src);
+    w.budget = a.take<float>(P * max_src);
     w.d2 = a.take<double>(P * max_src);
     w.partial = a.take<double>(P * w.src_rows * 16);
     w.amom = a.take<double>(P * 16);
@@ -113,6 +116,7 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     if (pair >= w.n_pairs) return;
     PairState s;
     for (int k = 0; k < 12; k++) s.T[k] = init_pose ? init_pose[(size_t)pair * 16 + k] : ((k % 5 == 0) ? 1.0 : 0.0);
+    for (int k = 0; k < 12; k++) s.Tp[k] = s.T[k];
     s.prev_err = 0.0;
     s.mean_err = 0.0;
     s.tau = CUDART_INF;      // keep everything until select_kernel says otherwise
@@ -492,12 +496,31 @@ nn_kernel(IcpWorkspace w, int write_d2) {
 
 // Lean variant (lean_search.cuh): a task is 32 consecutive queries of the sorted source cloud; no
 // group table.  Same virtual-warp scheme, so the moment sums are independent of the launch geometry.
+//
+// Skipping searches that cannot change the answer.  When a seeded search ends with the seed p still the
+// nearest point, it also knows a lower bound L2 of the distance to every OTHER point (the runner-up among
+// the evaluated points, or the radius it covered, whichever is smaller).  budget = L2 - d(q, p) is then
+// how much slack the answer has: if the query later moves by delta in total, p's distance grows by at
+// most delta and every other distance shrinks by at most delta (triangle inequality), so while
+// budget - 2 * sum(delta) > 0 the neighbour is still p, strictly, and no search is needed -- only the
+// exact new distance to p.  The per-iteration movement |T_k a - T_{k-1} a| is computed exactly per query
+// and subtracted from the stored budget with outward rounding.  To have a budget worth keeping, a seeded
+// lane asks for a ball a little larger than its bound (`slack`, proportional to its current movement):
+// costs a few candidates now, saves whole searches once ICP has nearly converged.
+struct LeanTuning {
+    float slack_mult;        // slack = slack_mult * (movement of the query in this iteration) ...
+    float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother)
+};
+
+// (Packing the lanes that still need a search into full warps through a per-warp queue was tried and
+// measured slower -- 339 vs 302 us per launch: the packed warps span several tasks, so their union boxes
+// grow as fast as the number of searches shrinks; profiles/r01_nn_sweeps.md, sweep_8.)
 template <bool SEEDED, bool FUSED>
 __global__ void __launch_bounds__(NN_THREADS, R3D_LEAN_MIN_CTAS)
-nn_lean_kernel(IcpWorkspace w, int write_d2) {
+nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
-    __shared__ double T[12];
+    __shared__ double T[12], D[12];
     __shared__ int s_n, s_done;
     __shared__ __align__(16) double scratch[NN_THREADS / 32][16 * 33];     // moment reduction scratch
     // survivors list of each warp; never shared with the reduction: its stale slots must stay real points
@@ -507,15 +530,20 @@ nn_lean_kernel(IcpWorkspace w, int write_d2) {
         s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
     }
-    if (threadIdx.x < 12) T[threadIdx.x] = w.state[pair].T[threadIdx.x];
+    if (threadIdx.x < 12) {
+        T[threadIdx.x] = w.state[pair].T[threadIdx.x];
+        D[threadIdx.x] = w.state[pair].T[threadIdx.x] - w.state[pair].Tp[threadIdx.x];
+    }
     __syncthreads();
     if (s_done) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GridView v = grid_view(w.grid, pair);
     const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
     int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
+    float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
     const int n_tasks = (s_n + 31) >> 5;
+    const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
     list_init(lists[warp], v.pts);
     while (true) {
@@ -528,22 +556,51 @@ nn_lean_kernel(IcpWorkspace w, int write_d2) {
             const int i = task * 32 + lane;
             const bool active = i < s_n;
             double qx = 0.0, qy = 0.0, qz = 0.0;
-            Best best;
-            best.d2 = CUDART_INF;
-            best.idx = 0x7fffffff;
-            best.pos = -1;      // no seed: no sorted position to exclude from the scan
+            Best seed, other;
+            seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
+            other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
+            float left = 0.0f, slack = 0.0f;      // budget left after this iteration's movement
+            bool skip = false;
             if (active) {
                 const Point4 a = load_point(src + i);
                 qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
                 qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
                 qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-                if (SEEDED) consider(best, v.pts, nn_pos[i], qx, qy, qz);
+                if (SEEDED) {
+                    consider(seed, v.pts, nn_pos[i], qx, qy, qz);
+                    const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
+                    const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
+                    const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
+                    // rounded up, with room for the rounding of the two transformed positions themselves
+                    const float moved = __double2float_ru(sqrt(mx * mx + my * my + mz * mz)) * 1.000001f + 1e-30f;
+                    left = __fsub_rd(budget[i], __fmul_ru(2.0f, moved));
+                    skip = left > 0.0f;
+                    const float want = moved * tune.slack_mult;
+                    slack = (want <= slack_max) ? want + 1e-4f * slack_max : 0.0f;
+                }
             }
             R3D_STAT(0, 1);
-            lean_search(lists[warp], best, v, g, active, qx, qy, qz);
+            float cover = 0.0f;
+            lean_search(lists[warp], seed, other, v, g, active && !skip, qx, qy, qz, slack, cover);
+            const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
+#ifdef R3D_NN_STATS
+            R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip)));
+            // a skipped lane still evaluates the warp's candidates: none of them may beat its seed
+            R3D_STAT(7, __popc(__ballot_sync(0xffffffffu, active && skip && (other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx)))));
+#endif
+            const Best best = seed_wins ? seed : other;
             if (active) {
                 nn_pos[i] = best.pos;
                 if (!FUSED || write_d2) d2_out[i] = best.d2;
+                float nb = 0.0f;
+                if (skip) {
+                    nb = left;
+                } else if (SEEDED && seed_wins) {
+                    // lower bound of the distance to any point other than the seed, minus the seed's distance
+                    const float l2 = fminf(__double2float_rd(sqrt(other.d2)), cover) * 0.999999f;
+                    nb = fmaxf(__fsub_rd(l2, __double2float_ru(sqrt(seed.d2)) * 1.000001f), 0.0f);
+                }
+                budget[i] = nb;
             }
             if (FUSED) {
                 double m[16];
@@ -744,7 +801,7 @@ solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
                 Tn[r * 4 + c] = acc;
             }
         }
-        for (int k = 0; k < 12; k++) st->T[k] = Tn[k];
+        for (int k = 0; k < 12; k++) { st->Tp[k] = st->T[k]; st->T[k] = Tn[k]; }
         const double mean = m[15] / cnt;
         st->mean_err = mean;
         if (fabs(st->prev_err - mean) < tolerance) {
@@ -901,13 +958,18 @@ static int launch_nn_g(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int 
 
 static std::atomic<int> g_nn_impl{1};      // 1 = lean walk (lean_search.cuh), 0 = staged lists (coop_search.cuh)
 
+static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f};
+
 static int launch_lean(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+    LeanTuning tune;
+    tune.slack_mult = g_slack_mult.load();
+    tune.slack_max_frac = g_slack_max_frac.load();
     if (seeded) {
-        if (fused) R3D_LAUNCH((nn_lean_kernel<true, true>), grid, NN_THREADS, 0, st, w, write_d2);
-        else R3D_LAUNCH((nn_lean_kernel<true, false>), grid, NN_THREADS, 0, st, w, write_d2);
+        if (fused) R3D_LAUNCH((nn_lean_kernel<true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        else R3D_LAUNCH((nn_lean_kernel<true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
     } else {
-        if (fused) R3D_LAUNCH((nn_lean_kernel<false, true>), grid, NN_THREADS, 0, st, w, write_d2);
-        else R3D_LAUNCH((nn_lean_kernel<false, false>), grid, NN_THREADS, 0, st, w, write_d2);
+        if (fused) R3D_LAUNCH((nn_lean_kernel<false, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        else R3D_LAUNCH((nn_lean_kernel<false, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
     }
     return R3D_OK;
 }
@@ -1098,6 +1160,14 @@ extern "C" int r3d_set_option(int option, double value) {
             g_nn_impl.store(impl);
             return R3D_OK;
         }
+        case R3D_OPT_SLACK_MULT:
+            if (!(value >= 0.0 && value <= 1.0e6)) return R3D_ERR_INVALID;
+            g_slack_mult.store((float)value);
+            return R3D_OK;
+        case R3D_OPT_SLACK_MAX_FRAC:
+            if (!(value >= 0.0 && value <= 64.0)) return R3D_ERR_INVALID;
+            g_slack_max_frac.store((float)value);
+            return R3D_OK;
         case R3D_OPT_CELL_FACTOR:
             if (!(value > 0.05 && value < 100.0)) return R3D_ERR_INVALID;
             g_cell_factor.store(value);

@@ -37,9 +37,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif
 
 // Diagnostic counters (builds with -DR3D_NN_STATS only; read by r3d_nn_stats_read):
-//   0 tasks  1 search rounds  2 candidate evaluations per lane  3 rounds with per-lane fallback
+//   0 tasks  1 search rounds  2 candidate evaluations per lane  3 lanes whose search was skipped
 //   4 segment lookup rounds   5 segments looked up              6 non-empty segments
-//   7 candidates loaded (before the box filter)
+//   7 skipped lanes whose seed was beaten by an evaluated point (a violated bound: must stay 0)
 #ifdef R3D_NN_STATS
 static __device__ unsigned long long g_nn_stats[8];      // this header is included by icp.cu only
 #define R3D_STAT(slot, n)                                                                   \
@@ -51,17 +51,22 @@ static __device__ unsigned long long g_nn_stats[8];      // this header is inclu
 #define R3D_STAT(slot, n) do { } while (0)
 #endif
 
-// one candidate of the list: xy = (x, y), zw = (z, cloud index | sorted position << 32)
+// one candidate of the list: xy = (x, y), zw = (z, cloud index | sorted position << 32).
+// `other` is the lexicographic minimum of (squared distance, cloud index) over every evaluated point
+// EXCEPT the lane's seed (sorted position seed_pos; -1 = none): the seed's exact distance is known
+// before the scan, and keeping the two apart is what yields the distance to the second-nearest point
+// whenever the seed stays the nearest (lean_search, "budget").
 // (ptxas turns the update into predicated moves whatever the source says -- a vote-guarded branch was
 // measured slower, profiles/r01_nn_sweeps.md -- so the test is kept minimal)
-__device__ __forceinline__ void eval_staged(Best& best, const double2 xy, const double2 zw, double qx, double qy, double qz) {
+__device__ __forceinline__ void eval_staged(Best& other, int seed_pos, const double2 xy, const double2 zw, double qx, double qy,
+                                            double qz) {
     const double dx = qx - xy.x, dy = qy - xy.y, dz = qz - zw.x;
     const double d2 = dx * dx + dy * dy + dz * dz;
-    const int idx = __double2loint(zw.y);
-    if (d2 < best.d2 || (d2 == best.d2 && idx < best.idx)) {
-        best.d2 = d2;
-        best.idx = idx;
-        best.pos = __double2hiint(zw.y);
+    const int idx = __double2loint(zw.y), pos = __double2hiint(zw.y);
+    if (pos != seed_pos && (d2 < other.d2 || (d2 == other.d2 && idx < other.idx))) {
+        other.d2 = d2;
+        other.idx = idx;
+        other.pos = pos;
     }
 }
 
@@ -74,7 +79,7 @@ struct WarpList {
 
 // Every lane scans the list, four entries at a time.  Slots past n hold points of earlier batches (or
 // the point the list was initialised with): real points of the same cloud, harmless to re-evaluate.
-__device__ __forceinline__ void list_flush(WarpList& L, Best& best, double qx, double qy, double qz) {
+__device__ __forceinline__ void list_flush(WarpList& L, Best& best, int seed_pos, double qx, double qy, double qz) {
     __syncwarp();
     const int n = L.n;
     R3D_STAT(2, (n + 3) & ~3);
@@ -82,10 +87,10 @@ __device__ __forceinline__ void list_flush(WarpList& L, Best& best, double qx, d
     for (int u = 0; u < n; u += 4) {
         const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + 1], b1 = L.szw[u + 1];
         const double2 a2 = L.sxy[u + 2], b2 = L.szw[u + 2], a3 = L.sxy[u + 3], b3 = L.szw[u + 3];
-        eval_staged(best, a0, b0, qx, qy, qz);
-        eval_staged(best, a1, b1, qx, qy, qz);
-        eval_staged(best, a2, b2, qx, qy, qz);
-        eval_staged(best, a3, b3, qx, qy, qz);
+        eval_staged(best, seed_pos, a0, b0, qx, qy, qz);
+        eval_staged(best, seed_pos, a1, b1, qx, qy, qz);
+        eval_staged(best, seed_pos, a2, b2, qx, qy, qz);
+        eval_staged(best, seed_pos, a3, b3, qx, qy, qz);
     }
     __syncwarp();
     L.n = 0;
@@ -107,8 +112,8 @@ __device__ __forceinline__ void list_init(double2* list, const Point4* __restric
 }
 
 // Walk every cell of the warp's box [lo, hi] (warp-uniform ints, at most LEAN_SEG_CAP segments).
-__device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, const GridView& v, const GridParams& g, int lox, int loy,
-                                              int loz, int hix, int hiy, int hiz, double qx, double qy, double qz) {
+__device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_pos, const GridView& v, const GridParams& g, int lox,
+                                              int loy, int loz, int hix, int hiy, int hiz, double qx, double qy, double qz) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     const int ny = hiy - loy + 1, nz = hiz - loz + 1;
@@ -150,7 +155,6 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, const Gri
         const uint32_t excl = incl - cnt;
         const uint32_t total = __shfl_sync(FULL, incl, 31);
         R3D_STAT(6, __popc(__ballot_sync(FULL, cnt > 0)));
-        R3D_STAT(7, total);
         if (total == 0u) continue;
         double2 xy = make_double2(0.0, 0.0), zw = make_double2(0.0, 0.0);
         bool have = false;
@@ -185,25 +189,32 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, const Gri
             }
             L.n += __popc(bal);
             if (t0 + 32 < total) fetch(t0 + 32);          // next batch's loads fly while the list is scanned
-            if (L.n >= LEAN_FLUSH) list_flush(L, best, qx, qy, qz);
+            if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
         }
     }
-    if (L.n > 0) list_flush(L, best, qx, qy, qz);
+    if (L.n > 0) list_flush(L, best, seed_pos, qx, qy, qz);
 }
 
-// Exact NN for the warp's 32 queries.  `best` holds a valid upper bound (a real point of the cloud)
-// for lanes that have one, d2 = +inf otherwise.  Inactive lanes take part in the collectives only.
-// `list`: 2 * LEAN_LIST_CAP double2 of shared memory owned by the warp.
+// Exact NN for the warp's 32 queries.
+//   seed    a real point of the cloud with its exact squared distance (the previous iteration's
+//           neighbour), or d2 = +inf / pos = -1 when the lane has none;
+//   other   out: lexicographic minimum over every evaluated point except the seed (d2 = +inf if none).
+//           The lane's nearest neighbour is the lexicographic minimum of seed and other;
+//   slack   extra radius (>= 0) a seeded lane asks for beyond its bound;
+//   cover   out: every point within this distance of the query was evaluated (0 = no claim).  With
+//           cover and other, sqrt(other.d2) and cover are both lower bounds of the distance to any
+//           point that is not the seed, which is what the caller's skip test needs.
+// Inactive lanes take part in the collectives only.  `list`: 2 * LEAN_LIST_CAP double2 of shared memory
+// owned by the warp.
 //
-// Expanding search in rounds.  Every unfinished lane asks for the ball of radius min(its bound, its
-// rcap), i.e. a box of cells.  Consecutive queries are usually neighbours in space, but a run of 32
+// Expanding search in rounds.  Every unfinished lane asks for the ball of radius min(its bound + slack,
+// its rcap), i.e. a box of cells.  Consecutive queries are usually neighbours in space, but a run of 32
 // can straddle two blocks that are far apart (a surface leaves and re-enters a row of blocks), so a
 // round serves the lanes around a LEADER (the first unfinished lane): those whose box lies inside a
 // window around the leader's.  The union box of the served lanes is walked; a served lane is
 // finished once its best distance is within the radius it asked for (nothing unseen can be closer),
 // otherwise its rcap doubles.  Lanes left out wait for a later round with a leader near them.  Lanes
-// that arrive with a bound (the previous iteration's neighbour) ask for their full ball at once, so a
-// coherent warp takes one round.
+// that arrive with a seed ask for their full ball at once, so a coherent warp takes one round.
 constexpr int LEAN_WIN = 4;      // served: box inside the leader's box widened by max(4 cells, its own extent)
 
 // float -> int map that preserves order under SIGNED comparison (and is its own inverse)
@@ -218,8 +229,8 @@ __device__ __forceinline__ float wmax_f(float v) { return sord2f(__reduce_max_sy
 __device__ __forceinline__ int cell_lo(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 
-__device__ __forceinline__ void lean_search(double2* list, Best& best, const GridView& v, const GridParams& g, bool active,
-                                            double qx, double qy, double qz) {
+__device__ __forceinline__ void lean_search(double2* list, const Best& seed, Best& other, const GridView& v, const GridParams& g,
+                                            bool active, double qx, double qy, double qz, float slack, float& cover) {
     // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
     // margin: 2e-3 cells absolute plus 2.4e-7 relative to the coordinate (one float ulp), on top of the
     // 1e-6 relative slack of the radius.
@@ -237,16 +248,17 @@ __device__ __forceinline__ void lean_search(double2* list, Best& best, const Gri
     L.sxy = list;
     L.szw = list + LEAN_LIST_CAP;
     L.n = 0;
-    float rcap = (best.d2 < CUDART_INF) ? inf : (float)g.cell;
+    float rcap = (seed.d2 < CUDART_INF) ? inf : (float)g.cell;
     bool fin = !active;
+    cover = 0.0f;
     while (true) {
         const unsigned unfin = __ballot_sync(FULL, !fin);
         if (unfin == 0u) return;
         R3D_STAT(1, 1);
         const int leader = __ffs(unfin) - 1;
         // float sqrt rounded up
-        const float rl = sqrtf((float)best.d2) * 1.000001f + 1e-30f;
-        const float ruse = fminf(rl, rcap);
+        const float rl = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
+        const float ruse = fminf(rl + slack, rcap);
         const float rc = ruse * inv_cell;
         const int mlox = cell_lo(tqx - rc - mgx, g.nx), mhix = cell_hi(tqx + rc + mgx, g.nx);
         const int mloy = cell_lo(tqy - rc - mgy, g.ny), mhiy = cell_hi(tqy + rc + mgy, g.ny);
@@ -274,18 +286,20 @@ __device__ __forceinline__ void lean_search(double2* list, Best& best, const Gri
             L.lo[0] = whole ? -CUDART_INF : (double)l0; L.hi[0] = whole ? CUDART_INF : (double)h0;
             L.lo[1] = whole ? -CUDART_INF : (double)l1; L.hi[1] = whole ? CUDART_INF : (double)h1;
             L.lo[2] = whole ? -CUDART_INF : (double)l2; L.hi[2] = whole ? CUDART_INF : (double)h2;
-            lean_scan_box(L, best, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
+            lean_scan_box(L, other, seed.pos, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
             if (part) {
-                const float rn = sqrtf((float)best.d2) * 1.000001f + 1e-30f;
+                const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                 fin = whole || (rn <= ruse) || !(ruse < 1e37f);
+                if (fin) cover = whole ? inf : ruse;
                 rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the union) must not set the next radius
             }
         } else {
-            R3D_STAT(3, 1);
             if (part) {
                 // far outliers / queries far outside the cloud: per-lane exact search with the block-list mode
-                if (!(best.d2 < CUDART_INF)) seed_search(best, v, g, qx, qy, qz);
-                bounded_search(best, v, g, qx, qy, qz);
+                Best b = (other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx)) ? other : seed;
+                if (!(b.d2 < CUDART_INF)) seed_search(b, v, g, qx, qy, qz);
+                bounded_search(b, v, g, qx, qy, qz);
+                if (b.pos != seed.pos) other = b;      // the exact neighbour; nothing is known about the runner-up
                 fin = true;
             }
             __syncwarp();

@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "8")))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "2")))
     ap.add_argument("--partial", type=float, default=1.0)
-    ap.add_argument("--cpu-sample-iters", type=int, default=8,
+    ap.add_argument("--cpu-sample-iters", type=int, default=16,
                     help="ICP iterations per pair of the bounded CPU sample (~1.3 s per iteration per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()

@@ -203,8 +203,12 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
 /* Tuning knobs; none of them changes results.  R3D_OPT_GROUP_SIZE: lanes that share one staged
  * candidate list in the NN search (8, 16 or 32).  R3D_OPT_CELL_FACTOR: automatic grid cell edge in
  * units of the estimated point spacing (used when cell_size <= 0).  R3D_OPT_NN_IMPL: 1 = lean
- * group-union walk (default), 0 = staged candidate lists. */
-typedef enum { R3D_OPT_GROUP_SIZE = 1, R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3 } r3d_option;
+ * group-union walk (default), 0 = staged candidate lists.  R3D_OPT_SLACK_MULT / R3D_OPT_SLACK_MAX_FRAC: how
+ * much larger than its bound a seeded search ball is made (multiple of the query's movement in this
+ * iteration, capped at a fraction of the cell edge; 0 disables search skipping). */
+typedef enum {
+    R3D_OPT_GROUP_SIZE = 1, R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5
+} r3d_option;
 int r3d_set_option(int option, double value);
 
 /* Number of kernels this library has launched since load (all entry points). */
@@ -219,8 +223,8 @@ int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* queries, in
 
 /* Diagnostic counters of the nn search (only in builds with -DR3D_NN_STATS, otherwise returns
  * R3D_ERR_INVALID): out8_host[0..7] = tasks (warps of 32 queries), search rounds, candidate
- * evaluations per lane, staged rounds, segment lookup rounds, segments looked up, non-empty
- * segments walked, reserved.  Synchronous. */
+ * evaluations per lane, searches skipped (lanes), segment lookup rounds, segments looked up, non-empty
+ * segments, skipped lanes whose seed was beaten by an evaluated point (must be 0).  Synchronous. */
 int r3d_nn_stats_read(uint64_t* out8_host, int reset);
 
 #ifdef __cplusplus

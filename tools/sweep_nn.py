@@ -32,7 +32,11 @@ a, b = bench.synth_batch_torch(pairs, 0, torch.device("cuda", 0))
 kw = dict(max_iterations=iters, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)
 ref = None
 for cfg in configs.split(","):
-    impl, group, factor = cfg.split(":")
+    parts = cfg.split(":")
+    impl, group, factor = parts[:3]
+    mult, maxfrac = (parts[3], parts[4]) if len(parts) >= 5 else ("8", "0.25")
+    assert L.r3d_set_option(4, float(mult)) == 0
+    assert L.r3d_set_option(5, float(maxfrac)) == 0
     assert L.r3d_set_option(3, float(impl)) == 0
     assert L.r3d_set_option(1, float(group)) == 0
     assert L.r3d_set_option(2, float(factor)) == 0
@@ -52,15 +56,16 @@ for cfg in configs.split(","):
         ref = T
     dev = float((T - ref).abs().max())
     nq = int(out["n_src"].sum())
-    print("impl %s G %2s factor %s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
+    print("impl %s G %2s factor %s slack %sx<=%s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
           "%.2f G corr/s in kernel | max|T - T0| %.2e err0 %.6f" % (
-              impl, group, factor, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
+              impl, group, factor, mult, maxfrac, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
               nq * n.value / max(ms.value, 1e-9) / 1e6, dev, float(out["mean_err"][0])), flush=True)
     if stats_on:
         st = (ctypes.c_uint64 * 8)()
         L.r3d_nn_stats_read(st, 1)
         tasks = max(int(st[0]), 1)
-        print("    per task of 32 queries: rounds %.2f, candidates/lane %.1f, staged rounds %.3f, lookup rounds %.2f, "
-              "segments %.1f, non-empty %.1f" % (st[1] / tasks, st[2] / tasks, st[3] / tasks, st[4] / tasks, st[5] / tasks,
-                                                 st[6] / tasks), flush=True)
+        print("    per task of 32 queries: rounds %.2f, candidates/lane %.1f, lanes skipped %.2f, lookup rounds %.2f, "
+              "segments %.1f, non-empty %.1f | violated skip bounds: %d" % (
+                  st[1] / tasks, st[2] / tasks, st[3] / tasks, st[4] / tasks, st[5] / tasks, st[6] / tasks, st[7]), flush=True)
+        assert st[7] == 0, "a skipped lane saw a point closer than its seed"
     assert dev < 1e-9, "variants disagree"
