@@ -7,7 +7,7 @@
 //                    the previous neighbour (the cloud moves little between iterations, so the
 //                    search box is ~1-2 cells wider than the warp's footprint).  With
 //                    partial_set_size == 1 the 16 Kabsch moments are reduced in the same kernel.
-//   select_kernel    (partial < 1) radix-select of the cutoff-th smallest squared distance
+//   sel_hist/pick    (partial < 1) radix-select of the cutoff-th smallest squared distance
 //                    = np.argpartition(distances, cutoff-1)[:cutoff], utils/icp.py:109-110
 //   moments_kernel   (partial < 1) moments over the kept correspondences
 //   solve_kernel     fixed-order sum of the per-CTA partials, 3x3 Kabsch (utils/icp.py:22-55),
@@ -38,6 +38,13 @@ struct PairState {
     int pad;
 };
 
+struct SelState {          // radix-select progress of one pair
+    unsigned long long prefix;
+    uint32_t k;            // rank still to find inside the prefix
+    uint32_t neq;          // keys in the chosen bin
+    int pad[2];
+};
+
 struct IcpWorkspace {
     GridWorkspace grid;
     int n_pairs, max_src, src_tiles, src_rows;
@@ -62,6 +69,8 @@ struct IcpWorkspace {
     double* d2;            // [pair][max_src]
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
+    SelState* sel;         // [pair]
+    uint32_t* sel_hist;    // [pair][SEL_PASSES][SEL_BINS]  zero between selections
 };
 
 static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int max_src, int max_dst) {
@@ -106,6 +115,8 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.d2 = a.take<double>(P * max_src);
     w.partial = a.take<double>(P * w.src_rows * 16);
     w.amom = a.take<double>(P * 16);
+    w.sel = a.take<SelState>(P);
+    w.sel_hist = a.take<uint32_t>(P * 6 * 2048);      // SEL_PASSES x SEL_BINS
     return a.used;
 }
 
@@ -119,7 +130,7 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     for (int k = 0; k < 12; k++) s.Tp[k] = s.T[k];
     s.prev_err = 0.0;
     s.mean_err = 0.0;
-    s.tau = CUDART_INF;      // keep everything until select_kernel says otherwise
+    s.tau = CUDART_INF;      // keep everything until the selection says otherwise
     s.idx_cut = 0x7fffffff;
     s.iters = 1;
     s.done = 0;
@@ -619,77 +630,125 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
 }
 
 // ---- partial-set selection ---------------------------------------------------------------------------
-// k-th smallest of the non-negative doubles d2[0..n) by MSB-first 8-bit radix select on their bit
-// patterns (order preserving for non-negative IEEE doubles).  One CTA per pair.
+// k-th smallest of the non-negative doubles d2[0..n) by MSB-first radix select on their bit patterns
+// (order preserving for non-negative IEEE doubles): 9 + 5 x 11 bits.  Every pass is a wide histogram
+// kernel over all keys that still match the prefix (shared-memory bins, warp-aggregated, merged into
+// the pair's global bins) followed by a one-CTA-per-pair pick of the bin that holds rank k.
+// = np.argpartition(distances, cutoff - 1)[:cutoff], utils/icp.py:109-110.
+constexpr int SEL_PASSES = 6;
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_TILE = 4096;      // keys per CTA of the histogram kernel
+__host__ __device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 55 : 55 - 11 * pass; }
+__host__ __device__ __forceinline__ int sel_bits(int pass) { return pass == 0 ? 9 : 11; }
+
+__global__ void __launch_bounds__(256)
+sel_hist_kernel(IcpWorkspace w, int pass) {
+    const int pair = blockIdx.y;
+    const PairState* st = w.state + pair;
+    const SelState sel = w.sel[pair];
+    const int n = st->n_src;
+    if (st->done || st->cutoff >= n || st->cutoff <= 0) return;      // nothing to select (see sel_pick_kernel)
+    const int base = blockIdx.x * SEL_TILE;
+    if (base >= n) return;
+    __shared__ uint32_t hist[SEL_BINS];
+    for (int k = threadIdx.x; k < SEL_BINS; k += 256) hist[k] = 0;
+    __syncthreads();
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(w.d2 + (size_t)pair * w.max_src);
+    const int shift = sel_shift(pass);
+    const uint32_t mask = (1u << sel_bits(pass)) - 1u;
+    const int lane = threadIdx.x & 31;
+#pragma unroll 4
+    for (int r = 0; r < SEL_TILE / 256; r++) {
+        const int i = base + r * 256 + threadIdx.x;
+        bool in = false;
+        uint32_t d = 0;
+        if (i < n) {
+            const unsigned long long key = keys[i];
+            in = (pass == 0) || ((key >> (shift + sel_bits(pass))) == sel.prefix);
+            d = (uint32_t)(key >> shift) & mask;
+        }
+        // lanes outside the prefix form singleton groups that never touch the bins
+        const unsigned grp = __match_any_sync(0xffffffffu, in ? d : (SEL_BINS + (uint32_t)lane));
+        if (in && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(grp));
+    }
+    __syncthreads();
+    uint32_t* gh = w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS;
+    for (int k = threadIdx.x; k < SEL_BINS; k += 256) {
+        const uint32_t c = hist[k];
+        if (c) atomicAdd(gh + k, c);
+    }
+}
+
+// one CTA per pair: find the bin that holds rank k, descend into it; after the last pass publish the
+// threshold and, when exact ties straddle the cutoff, the largest source index kept among them
 __global__ void __launch_bounds__(1024)
-select_kernel(IcpWorkspace w) {
+sel_pick_kernel(IcpWorkspace w, int pass) {
     const int pair = blockIdx.x;
     PairState* st = w.state + pair;
     if (st->done) return;
+    SelState* sel = w.sel + pair;
     const int n = st->n_src, cutoff = st->cutoff;
-    if (cutoff >= n || cutoff <= 0) {
-        if (threadIdx.x == 0) { st->tau = (cutoff >= n) ? CUDART_INF : -1.0; st->idx_cut = 0x7fffffff; }
-        return;
-    }
-    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(w.d2 + (size_t)pair * w.max_src);
-    __shared__ uint32_t hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ uint32_t s_k, s_neq;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t warp_cnt[32];
     __shared__ int s_idx_cut;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) { s_prefix = 0ull; s_k = (uint32_t)(cutoff - 1); }
-    const int n_round = (n + 1023) / 1024 * 1024;
-    for (int pass = 7; pass >= 0; pass--) {
-        const int shift = pass * 8;
-        if (threadIdx.x < 256) hist[threadIdx.x] = 0;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        for (int i = threadIdx.x; i < n_round; i += 1024) {
-            bool in = false;
-            uint32_t d = 0;
-            if (i < n) {
-                const unsigned long long key = keys[i];
-                in = (pass == 7) || ((key >> (shift + 8)) == prefix);
-                d = (uint32_t)(key >> shift) & 255u;
-            }
-            const unsigned grp = __match_any_sync(0xffffffffu, in ? d : (256u + (uint32_t)lane));
-            if (in && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(grp));
-        }
-        __syncthreads();
-        if (warp == 0) {
-            // 8 bins per lane; find the bin containing rank k
-            uint32_t c[8], tot = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
-            uint32_t x = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += y;
-            }
-            uint32_t before = x - tot;
-            const uint32_t k = s_k;
-            if (k >= before && k < before + tot) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (k >= before && k < before + c[j]) {
-                        s_prefix = (prefix << 8) | (unsigned long long)(lane * 8 + j);
-                        s_k = k - before;
-                        s_neq = c[j];
-                    }
-                    before += c[j];
-                }
-            }
+    // nothing to select: keep everything / nothing
+    const bool trivial = cutoff >= n || cutoff <= 0;
+    if (pass == 0) {
+        if (threadIdx.x == 0) {
+            sel->prefix = 0ull;
+            sel->k = (uint32_t)max(cutoff - 1, 0);
+            if (trivial) { st->tau = (cutoff >= n) ? CUDART_INF : -1.0; st->idx_cut = 0x7fffffff; }
         }
         __syncthreads();
     }
-    const unsigned long long tau_bits = s_prefix;
-    const uint32_t quota = s_k + 1;     // how many elements equal to tau belong to the kept set
+    if (trivial) return;
+    uint32_t* gh = w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS;
+    // 2 bins per thread, exclusive scan over the CTA
+    const uint32_t c0 = gh[2 * threadIdx.x], c1 = gh[2 * threadIdx.x + 1];
+    gh[2 * threadIdx.x] = 0;          // ready for the next iteration's selection
+    gh[2 * threadIdx.x + 1] = 0;
+    const uint32_t tot = c0 + c1;
+    uint32_t x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t t = warp_tot[lane];
+        uint32_t ts = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
+            if (lane >= o) ts += y;
+        }
+        warp_tot[lane] = ts - t;
+    }
+    __syncthreads();
+    const uint32_t before = warp_tot[warp] + x - tot;
+    const uint32_t k = sel->k;
+    const unsigned long long prefix = sel->prefix;
+    __syncthreads();
+    if (k >= before && k < before + tot) {          // exactly one thread
+        const bool first = k < before + c0;
+        const uint32_t bin = 2 * threadIdx.x + (first ? 0 : 1);
+        sel->prefix = (prefix << sel_bits(pass)) | (unsigned long long)bin;
+        sel->k = k - before - (first ? 0u : c0);
+        sel->neq = first ? c0 : c1;
+    }
+    if (pass != SEL_PASSES - 1) return;
+    __syncthreads();
+    const unsigned long long tau_bits = sel->prefix;
+    const uint32_t quota = sel->k + 1;     // how many elements equal to tau belong to the kept set
+    const uint32_t neq = sel->neq;
     if (threadIdx.x == 0) s_idx_cut = 0x7fffffff;
     __syncthreads();
-    if (quota < s_neq) {
+    if (quota < neq) {
         // exact ties straddle the cutoff: keep the lowest-index `quota` of them
+        const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(w.d2 + (size_t)pair * w.max_src);
         uint32_t running = 0;
         for (int start = 0; start < n; start += 1024) {
             const int i = start + threadIdx.x;
@@ -697,13 +756,13 @@ select_kernel(IcpWorkspace w) {
             const unsigned bal = __ballot_sync(0xffffffffu, eq);
             if (lane == 0) warp_cnt[warp] = __popc(bal);
             __syncthreads();
-            uint32_t before = running;
-            for (int wv = 0; wv < warp; wv++) before += warp_cnt[wv];
-            const uint32_t incl = before + __popc(bal & ((2u << lane) - 1u));
+            uint32_t bef = running;
+            for (int wv = 0; wv < warp; wv++) bef += warp_cnt[wv];
+            const uint32_t incl = bef + __popc(bal & ((2u << lane) - 1u));
             if (eq && incl == quota) s_idx_cut = i;
-            uint32_t tot = 0;
-            for (int wv = 0; wv < 32; wv++) tot += warp_cnt[wv];
-            running += tot;
+            uint32_t t2 = 0;
+            for (int wv = 0; wv < 32; wv++) t2 += warp_cnt[wv];
+            running += t2;
             __syncthreads();
         }
     }
@@ -1014,6 +1073,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
     R3D_LAUNCH(src_moments_reduce_kernel, P, SOLVE_THREADS, 0, st, w);
     const bool fused = prm.partial_set_size >= 1.0 && !getenv("R3D_FORCE_UNFUSED");
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
+    if (!fused) R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * SEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
     for (int it = 0; it < prm.max_iterations; it++) {
         {
             NnTimer timer(st);
@@ -1021,7 +1081,10 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
             if (rc != R3D_OK) return rc;
         }
         if (!fused) {
-            R3D_LAUNCH(select_kernel, P, 1024, 0, st, w);
+            for (int pass = 0; pass < SEL_PASSES; pass++) {
+                R3D_LAUNCH(sel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
+                R3D_LAUNCH(sel_pick_kernel, P, 1024, 0, st, w, pass);
+            }
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
         }
         R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? NN_VWARPS : 0);

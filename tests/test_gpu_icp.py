@@ -151,3 +151,57 @@ def test_one_iteration_consistency_over_sizes(n, partial):
     moved = (T_iter[:3, :3] @ A.T).T + T_iter[:3, 3]
     T_want = O.best_fit_transform(A, moved)               # utils/icp.py:131
     assert_transform_parity(r["T"][0].cpu().numpy(), T_want, O.scene_extent(B), "n=%d" % n, 1e-8, 1e-9)
+
+
+def test_search_skipping_and_search_variants_do_not_change_results():
+    """The nn search has tuning knobs (skip budgets, the staged vs warp-union walk); none may change a
+    bit of the result: every variant is an exact search.  After 25 iterations -- when most lanes skip
+    their search -- the exported correspondences must still be brute force's."""
+    ops = sub("ops")
+    C = sub("_capi")
+    L = C.lib()
+    a, b = O.synth_depth_pair(5, h=120, w=160)
+    fa = np.zeros((480, 640), np.uint16)
+    fb = np.zeros((480, 640), np.uint16)
+    fa[180:300, 240:400] = a
+    fb[180:300, 240:400] = b
+    A, B = O.depth_to_voxel_ld(fa), O.depth_to_voxel_ld(fb)
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    so, do = ops._offsets([len(A)]), ops._offsets([len(B)])
+
+    def run(iters):
+        return ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=iters, tolerance=0.0, want_last=True)
+
+    try:
+        base = run(25)
+        Tb = base["T"].cpu().numpy()
+        for opt, val in ((4, 0.0), (4, 64.0), (5, 1.0), (3, 0.0)):     # no skipping; generous slack; large cap; staged walk
+            assert L.r3d_set_option(opt, val) == 0
+            r = run(25)
+            if opt == 3:
+                # the staged walk sums its moments in another order, so its poses differ in the last bits and an
+                # exact distance tie (quantised depth makes them real) may then fall the other way
+                np.testing.assert_allclose(r["T"].cpu().numpy(), Tb, rtol=0, atol=1e-9)
+                assert (r["idx"].cpu().numpy() != base["idx"].cpu().numpy()).mean() < 1e-3
+                np.testing.assert_allclose(r["dist"].cpu().numpy(), base["dist"].cpu().numpy(), rtol=1e-9, atol=1e-9)
+            else:
+                assert np.array_equal(r["T"].cpu().numpy(), Tb), (opt, val)
+                assert np.array_equal(r["idx"].cpu().numpy(), base["idx"].cpu().numpy()), (opt, val)
+                assert np.array_equal(r["dist"].cpu().numpy(), base["dist"].cpu().numpy()), (opt, val)
+            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0)
+    finally:
+        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0)
+    # the last iteration's correspondences against brute force: src of iteration 25 = T_24 * A, which is the
+    # pose after 24 iterations
+    T24 = run(24)["T"][0].cpu().numpy()
+    src = O.get_transformed_points(A, T24)
+    db, ib = O.nearest_neighbor_brute(src, B)
+    idx = base["idx"].cpu().numpy().astype(np.int64)
+    diff = np.nonzero(idx != ib)[0]
+    # T24 here is best_fit_transform(A, src_24) (icp.py:131), equal to the cumulative product up to rounding, so a
+    # handful of exact-tie flips are possible; anything else is a wrong neighbour
+    if diff.size:
+        d_mine = np.linalg.norm(src[diff] - B[idx[diff]], axis=1)
+        assert np.all(np.abs(d_mine - db[diff]) <= 1e-9 * np.maximum(db[diff], 1.0)), "wrong neighbour after skipping"
+    assert diff.size < 0.001 * len(A)

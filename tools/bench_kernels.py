@@ -1,0 +1,203 @@
+"""Per-kernel measurements for every row of SURVEY.md section 8 (secondary to bench.py's headline line).
+
+    python tools/bench_kernels.py > gpurun_out/kernels.json
+
+Each entry: what was run, CUDA-event time (median of 5 after 2 warm-ups, inputs larger than L2 or the L2
+flushed in between), the algorithmic work, and the fraction of the bound named in DESIGN.md section 3.
+Calls go through the C ABI directly with pre-allocated buffers, so the timed region is the library call only.
+"""
+import ctypes
+import importlib
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+C = importlib.import_module("2dto3dreconstruction_b200._capi")
+ops = importlib.import_module("2dto3dreconstruction_b200.ops")
+L = C.lib()
+C.require_device()
+dev = torch.device("cuda", 0)
+HBM, HBM_SRC = bench.peak_hbm()
+FP64_FLOPS = 148 * 64 * 2 * 1.965e9          # nominal non-tensor fp64, DESIGN.md section 3
+flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=5, warm=2, flush=True):
+    ts = []
+    for k in range(warm + reps):
+        if flush:
+            flush_buf.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if k >= warm:
+            ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+out = {"hbm_peak_gbs": HBM, "hbm_peak_source": HBM_SRC, "fp64_peak_tflops_nominal": FP64_FLOPS / 1e12}
+
+# ---- K1 back-projection: 64 frames 640x480 uint16 -> xyzw fp64 ---------------------------------------------
+F = 64
+a, _ = bench.synth_batch_torch(F, 0, dev)
+pts = torch.empty((F * 480 * 640, 4), dtype=torch.float64, device=dev)
+off = torch.empty(F + 1, dtype=torch.int32, device=dev)
+nws = L.r3d_backproject_workspace_bytes(F, 480, 640)
+ws = C.workspace(nws)
+st = C.stream_ptr()
+
+
+def k1():
+    C.check(L.r3d_backproject(C.ptr(a), 0, F, 480, 640, 1, 525.0, 525.0, 319.5, 239.5, 1.0, 1, C.ptr(pts), C.ptr(off), C.ptr(ws),
+                              nws, st))
+
+
+ms = timed(k1)
+nvalid = int(off[-1].item())
+algo = 2 * F * 480 * 640 + 32 * nvalid
+out["K1_backproject"] = {"what": "%d frames 640x480 u16 -> xyzw fp64, pinhole (3 launches: count, scan, write)" % F, "ms": ms,
+                         "frames_per_s": F / ms * 1e3, "algorithmic_bytes": algo, "achieved_gbs": algo / ms / 1e6,
+                         "frac_of_hbm": algo / ms / 1e6 / HBM,
+                         "note": "count re-reads the depth once more (2 B/pixel): traffic = algorithmic + 2*H*W per frame"}
+
+# ---- grid build + one unseeded query (r3d_nn_batch) on 8 pairs ----------------------------------------------
+P = 8
+fa, fb = bench.synth_batch_torch(P, 0, dev)
+sp = torch.empty((P * 480 * 640, 4), dtype=torch.float64, device=dev)
+dp = torch.empty((P * 480 * 640, 4), dtype=torch.float64, device=dev)
+so = torch.empty(P + 1, dtype=torch.int32, device=dev)
+do = torch.empty(P + 1, dtype=torch.int32, device=dev)
+nws2 = L.r3d_backproject_workspace_bytes(P, 480, 640)
+ws2 = C.workspace(nws2)
+C.check(L.r3d_backproject(C.ptr(fa), 0, P, 480, 640, 1, 525.0, 525.0, 319.5, 239.5, 1.0, 1, C.ptr(sp), C.ptr(so), C.ptr(ws2), nws2, st))
+C.check(L.r3d_backproject(C.ptr(fb), 0, P, 480, 640, 1, 525.0, 525.0, 319.5, 239.5, 1.0, 1, C.ptr(dp), C.ptr(do), C.ptr(ws2), nws2, st))
+torch.cuda.synchronize()
+nq = int(so[-1].item())
+hw = 480 * 640
+nnws = L.r3d_icp_workspace_bytes(P, hw, hw)
+wsn = C.workspace(nnws)
+idx = torch.empty(nq, dtype=torch.int32, device=dev)
+dist = torch.empty(nq, dtype=torch.float64, device=dev)
+
+
+def nn_once():
+    C.check(L.r3d_nn_batch(C.ptr(sp), C.ptr(so), C.ptr(dp), C.ptr(do), P, hw, hw, 0.0, C.ptr(idx), C.ptr(dist), C.ptr(wsn), nnws, st))
+
+
+L.r3d_nn_timing_enable(1)
+ms = timed(nn_once)
+tms, tn, tq = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+L.r3d_nn_timing_read(ctypes.byref(tms), ctypes.byref(tn), ctypes.byref(tq), 1)
+L.r3d_nn_timing_enable(0)
+q_ms = tms.value / max(tn.value, 1)
+out["K2_nn_batch_unseeded"] = {"what": "nearest_neighbor for 8 pairs x ~276k: grid build + source sort + one unseeded query + export",
+                               "ms": ms, "query_kernel_ms": q_ms, "build_sort_export_ms": ms - q_ms,
+                               "correspondences_per_s": nq / ms * 1e3, "query_correspondences_per_s": nq / q_ms * 1e3}
+
+
+# ---- ICP loop: 30 iterations on the same 8 pairs --------------------------------------------------------------
+T = torch.empty((P, 16), dtype=torch.float64, device=dev)
+it = torch.empty(P, dtype=torch.int32, device=dev)
+err = torch.empty(P, dtype=torch.float64, device=dev)
+for partial in (1.0, 0.7):
+    prm = C.IcpParams(30, 0, 0.0, partial, 0.0)
+
+    def icp30():
+        C.check(L.r3d_icp_batch(C.ptr(sp), C.ptr(so), C.ptr(dp), C.ptr(do), P, hw, hw, None, ctypes.byref(prm), C.ptr(T), C.ptr(it),
+                                C.ptr(err), None, None, None, C.ptr(wsn), nnws, st))
+
+    L.r3d_nn_timing_enable(1)
+    ms = timed(icp30)
+    L.r3d_nn_timing_read(ctypes.byref(tms), ctypes.byref(tn), ctypes.byref(tq), 1)
+    L.r3d_nn_timing_enable(0)
+    out["K2K3_icp_30it_partial_%.1f" % partial] = {
+        "what": "r3d_icp_batch, 8 pairs x ~276k, 30 iterations, tolerance 0, partial_set_size %.1f" % partial, "ms": ms,
+        "pairs_per_s": P / ms * 1e3, "correspondences_per_s": 30 * nq / ms * 1e3,
+        "nn_kernel_ms_per_launch": tms.value / max(tn.value, 1), "nn_kernel_share": tms.value / (ms * 7),
+        "mean_err": float(err.mean().item())}
+
+# ---- K3 Kabsch / K3c affine on 2 M given correspondences -------------------------------------------------------
+n = 2_000_000
+g = torch.Generator(device=dev).manual_seed(1)
+A = torch.randn((n, 3), dtype=torch.float64, device=dev, generator=g) * 500
+B = A + torch.randn((n, 3), dtype=torch.float64, device=dev, generator=g)
+kws = L.r3d_kabsch_workspace_bytes(n)
+wsk = C.workspace(kws)
+T1 = torch.empty(16, dtype=torch.float64, device=dev)
+
+
+def kab():
+    C.check(L.r3d_kabsch(C.ptr(A), 3, 1, C.ptr(B), 3, 1, n, C.ptr(T1), C.ptr(wsk), kws, st))
+
+
+ms = timed(kab)
+out["K3_kabsch"] = {"what": "best_fit_transform on 2 M pairs (packed (n,3) fp64)", "ms": ms, "algorithmic_bytes": 48 * n,
+                    "achieved_gbs": 48 * n / ms / 1e6, "frac_of_hbm": 48 * n / ms / 1e6 / HBM}
+aws = L.r3d_affine_fit_workspace_bytes(n)
+wsa = C.workspace(aws)
+stat = torch.empty(1, dtype=torch.int32, device=dev)
+
+
+def aff():
+    C.check(L.r3d_affine_fit(C.ptr(A), C.ptr(B), n, C.ptr(T1), C.ptr(stat), C.ptr(wsa), aws, st))
+
+
+ms = timed(aff)
+out["K3c_affine_fit"] = {"what": "homo_rigid_transform_3d on 2 M pairs", "ms": ms, "algorithmic_bytes": 48 * n,
+                         "achieved_gbs": 48 * n / ms / 1e6, "frac_of_hbm": 48 * n / ms / 1e6 / HBM}
+
+# ---- K4B: 100k hypotheses x 50k correspondences (configs[4]) ----------------------------------------------------
+nh, npnt = 100_000, 50_000
+Pp = torch.zeros((npnt, 4), dtype=torch.float64, device=dev)
+Pp[:, :3] = (torch.rand((npnt, 3), dtype=torch.float64, device=dev, generator=g) * 2000 - 1000)
+Qp = Pp.clone()
+Qp[:, :3] += torch.randn((npnt, 3), dtype=torch.float64, device=dev, generator=g)
+Hy = torch.eye(4, dtype=torch.float64, device=dev).repeat(nh, 1, 1).contiguous()
+Hy[:, :3, 3] = torch.randn((nh, 3), dtype=torch.float64, device=dev, generator=g)
+cnt = torch.empty(nh, dtype=torch.int32, device=dev)
+
+
+def k4b():
+    C.check(L.r3d_ransac3d_score(C.ptr(Hy), nh, C.ptr(Pp), C.ptr(Qp), npnt, 10.0, C.ptr(cnt), st))
+
+
+ms = timed(k4b, flush=False)
+ev = nh * npnt
+out["K4B_ransac3d_sweep"] = {"what": "100k rigid/affine 4x4 hypotheses x 50k correspondences, fp64", "ms": ms,
+                             "evaluations_per_s": ev / ms * 1e3, "fp64_flops_per_evaluation": 32,
+                             "achieved_tflops": 32 * ev / ms / 1e9, "frac_of_fp64_nominal": 32 * ev / ms * 1e3 / FP64_FLOPS}
+
+# ---- K4A: reference-exact 2-D scoring at its native size (100 hypotheses x 1100 keypoints) ---------------------
+rng = np.random.default_rng(3)
+n1 = n2 = 1100
+kp1 = np.column_stack((rng.uniform(0, 479, n1), rng.uniform(0, 639, n1)))
+kp2 = kp1 + rng.normal(0, 1.0, kp1.shape)
+Hs = np.tile(np.eye(3), (100, 1, 1)) + rng.normal(0, 1e-4, (100, 3, 3))
+Hd = C.to_device(Hs.reshape(100, 9))
+k1d, k2d = C.to_device(kp1), C.to_device(kp2)
+c2 = torch.empty(100, dtype=torch.int32, device=dev)
+fl = torch.empty(100, dtype=torch.int32, device=dev)
+w2 = L.r3d_ransac2d_workspace_bytes(100, n1, n2, 480, 640)
+ws2d = C.workspace(w2)
+
+
+def k4a():
+    C.check(L.r3d_ransac2d_score(C.ptr(Hd), None, 100, C.ptr(k1d), n1, C.ptr(k2d), n2, 480, 640, C.ptr(c2), None, None, C.ptr(fl),
+                                 C.ptr(ws2d), w2, st))
+
+
+ms = timed(k4a, flush=False)
+out["K4A_ransac2d"] = {"what": "q9.ransac_loop scoring body: 100 hypotheses x 1100 keypoints, 480x640 bins", "ms": ms,
+                       "hypotheses_per_s": 100 / ms * 1e3, "note": "the reference needs ~65 ms per hypothesis (SURVEY.md section 6)"}
+
+print(json.dumps(out, indent=1))
