@@ -53,8 +53,8 @@ __global__ void counts_kernel(const int32_t* __restrict__ src_off, const int32_t
     if (n_dst) n_dst[i] = dst_off[i + 1] - dst_off[i];
 }
 
-int default_ppc(int ppc) { return ppc > 0 ? ppc : 8; }
-int default_streams(int s) { return s > 0 ? (s > 4 ? 4 : s) : 2; }
+int default_ppc(int ppc) { return ppc > 0 ? ppc : 16; }
+int default_streams(int s) { return s > 0 ? (s > 4 ? 4 : s) : 3; }
 
 int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool host_input, int n_pairs, int h, int w, double fx,
                   double fy, double cx, double cy, const r3d_icp_params* params, int ppc, int n_streams, double* T_out,

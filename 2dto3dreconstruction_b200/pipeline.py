@@ -35,7 +35,7 @@ def pinned_like(shape, dtype):
 
 
 def register_depth_pairs(depth_src, depth_dst, max_iterations=30, tolerance=0.0, partial_set_size=1.0,
-                         pairs_per_chunk=8, n_streams=2, cell_size=0.0, fx=ops.FX, fy=ops.FY, cx=ops.CX, cy=ops.CY):
+                         pairs_per_chunk=16, n_streams=3, cell_size=0.0, fx=ops.FX, fy=ops.FY, cx=ops.CX, cy=ops.CY):
     """Register depth_src[p] onto depth_dst[p] for every pair p: pinhole back-projection of both
     frames (utils/utils.py:48-76), then ICP (utils/icp.py:74-133) of the source cloud onto the
     destination cloud.

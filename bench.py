@@ -42,8 +42,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("R3D_BENCH_PAIRS", "1024")), help="pairs per GPU")
-    ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "8")))
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "2")))
+    ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "16")))
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "3")))
     ap.add_argument("--partial", type=float, default=1.0)
     ap.add_argument("--cpu-sample-iters", type=int, default=16,
                     help="ICP iterations per pair of the bounded CPU sample (~1.3 s per iteration per core)")
@@ -242,6 +242,16 @@ def main():
     nn_ms, nn_launches, nn_q = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
     C.check(L.r3d_nn_timing_read(ctypes.byref(nn_ms), ctypes.byref(nn_launches), ctypes.byref(nn_q), 1))
 
+    # the same kernel timed alone on the GPU (one stream, one chunk in flight): the clean per-launch duration
+    L.r3d_nn_timing_enable(1)
+    solo_pairs = min(P, 2 * args.pairs_per_chunk)
+    pipeline.register_depth_pairs(depth_a[:solo_pairs], depth_b[:solo_pairs], max_iterations=ICP_ITERS, tolerance=0.0,
+                                  partial_set_size=args.partial, pairs_per_chunk=args.pairs_per_chunk, n_streams=1)
+    torch.cuda.synchronize()
+    L.r3d_nn_timing_enable(0)
+    solo_ms, solo_launches = ctypes.c_double(), ctypes.c_int64()
+    C.check(L.r3d_nn_timing_read(ctypes.byref(solo_ms), ctypes.byref(solo_launches), ctypes.byref(nn_q), 1))
+
     n_src = out["n_src"].cpu().numpy().astype(np.int64)
     iters = out["iters"].cpu().numpy().astype(np.int64)
     executed = np.minimum(iters, ICP_ITERS)               # iterations actually run per pair
@@ -302,16 +312,23 @@ def main():
         "bound": "hbm", "kernel": "nn_lean_kernel (K2 exact grid NN + fused K3 moments)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_correspondence": ALGO_BYTES_PER_CORR, "launches_timed": int(nn_launches.value),
-        "avg_launch_ms": nn_avg_ms, "kernel_share_of_step": nn_ms.value / ms_total,
+        "avg_launch_ms": nn_avg_ms, "kernel_share_of_step": nn_ms.value / (ms_total * args.streams),
+        "share_note": "sum of the kernel's event-bracketed time / (timed region x %d streams): launches of different streams "
+                      "overlap, so in-step durations include waiting for the other streams' kernels" % args.streams,
+        "avg_launch_ms_solo": solo_ms.value / max(solo_launches.value, 1),
+        "achieved_solo": ALGO_BYTES_PER_CORR * float(n_src[:solo_pairs].sum()) * ICP_ITERS / max(solo_ms.value / 1000.0, 1e-12) / 1e9,
         "correspondences_per_sec_in_kernel": corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12),
     }
     # what actually bounds the kernel: the FP64 pipe / issue slots of the candidate scan
-    fp64_instr_per_s = EVALS_PER_CORR * 6.0 / 32.0 * roofline["correspondences_per_sec_in_kernel"]
+    solo_corr_per_s = float(n_src[:solo_pairs].sum()) * ICP_ITERS / max(solo_ms.value / 1000.0, 1e-12)
+    roofline["correspondences_per_sec_in_kernel_solo"] = solo_corr_per_s
+    fp64_instr_per_s = EVALS_PER_CORR * 6.0 / 32.0 * solo_corr_per_s
     roofline["pipe"] = {"bound": "fp64 pipe (non-tensor)", "evaluations_per_correspondence": EVALS_PER_CORR,
                         "achieved_fp64_warp_instr_per_s": fp64_instr_per_s, "peak_fp64_warp_instr_per_s": FP64_WARP_INSTR_PER_S,
                         "frac": fp64_instr_per_s / FP64_WARP_INSTR_PER_S,
-                        "note": "nominal peak: 16 fp64 lanes/clk/SMSP x 592 SMSPs x 1965 MHz; evaluations per "
-                                "correspondence from the counter build (profiles/r01_nn_sweeps.md)"}
+                        "note": "kernel timed alone; nominal peak: 16 fp64 lanes/clk/SMSP x 592 SMSPs x 1965 MHz; evaluations "
+                                "per correspondence searched from the counter build (profiles/r01_nn_sweeps.md); skipped "
+                                "searches make the effective figure lower in late iterations"}
     traffic_file = os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
