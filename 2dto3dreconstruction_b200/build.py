@@ -29,7 +29,8 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ] + (["-DR3D_NN_MIN_CTAS=" + os.environ["R3D_NN_MIN_CTAS"]] if os.environ.get("R3D_NN_MIN_CTAS") else []) \
   + (["-DR3D_LEAN_MIN_CTAS=" + os.environ["R3D_LEAN_MIN_CTAS"]] if os.environ.get("R3D_LEAN_MIN_CTAS") else []) \
-  + (["-DR3D_NN_STATS"] if os.environ.get("R3D_NN_STATS") else [])
+  + (["-DR3D_NN_STATS"] if os.environ.get("R3D_NN_STATS") else []) \
+  + ["-D%s=%s" % (k, os.environ[k]) for k in ("R3D_LEAN_FLUSH", "R3D_LEAN_RCAP0") if os.environ.get(k)]
 
 
 def _nvcc():

@@ -583,7 +583,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
                     const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
                     // rounded up, with room for the rounding of the two transformed positions themselves
-                    const float moved = __double2float_ru(sqrt(mx * mx + my * my + mz * mz)) * 1.000001f + 1e-30f;
+                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f + 1e-30f;
                     left = __fsub_rd(budget[i], __fmul_ru(2.0f, moved));
                     skip = left > 0.0f;
                     const float want = moved * tune.slack_mult;
@@ -608,8 +608,9 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     nb = left;
                 } else if (SEEDED && seed_wins) {
                     // lower bound of the distance to any point other than the seed, minus the seed's distance
-                    const float l2 = fminf(__double2float_rd(sqrt(other.d2)), cover) * 0.999999f;
-                    nb = fmaxf(__fsub_rd(l2, __double2float_ru(sqrt(seed.d2)) * 1.000001f), 0.0f);
+                    // (float square roots: the 1e-6 factors cover their rounding)
+                    const float l2 = fminf(sqrtf(__double2float_rd(other.d2)), cover) * 0.999999f;
+                    nb = fmaxf(__fsub_rd(l2, sqrtf(__double2float_ru(seed.d2)) * 1.000001f), 0.0f);
                 }
                 budget[i] = nb;
             }

@@ -30,7 +30,10 @@ namespace r3d {
 
 constexpr int LEAN_SEG_CAP = 2048;     // segments per round the warp walk accepts
 constexpr int LEAN_LIST_CAP = 64;      // survivors list: at most LEAN_FLUSH - 1 + 32 entries between flushes
-constexpr int LEAN_FLUSH = 24;         // scan the list as soon as it holds this many points
+#ifndef R3D_LEAN_FLUSH
+#define R3D_LEAN_FLUSH 24
+#endif
+constexpr int LEAN_FLUSH = R3D_LEAN_FLUSH;      // scan the list as soon as it holds this many points (<= 32)
 #ifndef R3D_FULL_MASK_DEFINED
 #define R3D_FULL_MASK_DEFINED
 constexpr unsigned FULL = 0xffffffffu;
@@ -248,7 +251,10 @@ __device__ __forceinline__ void lean_search(double2* list, const Best& seed, Bes
     L.sxy = list;
     L.szw = list + LEAN_LIST_CAP;
     L.n = 0;
-    float rcap = (seed.d2 < CUDART_INF) ? inf : (float)g.cell;
+#ifndef R3D_LEAN_RCAP0
+#define R3D_LEAN_RCAP0 1.0f
+#endif
+    float rcap = (seed.d2 < CUDART_INF) ? inf : R3D_LEAN_RCAP0 * (float)g.cell;
     bool fin = !active;
     cover = 0.0f;
     while (true) {
