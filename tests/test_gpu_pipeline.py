@@ -84,3 +84,34 @@ def test_chain_matches_reference_prefix_product():
     want = O.chain_prefix(list(Ts))
     assert np.array_equal(pipeline.chain(Ts), np.stack(want))
     assert all(np.array_equal(a, b) for a, b in zip(rec.chain_prefix(list(Ts)), want))
+
+
+def test_sofa_pair_against_the_reference_run():
+    """BASELINE.json configs[0], one pair: the CUDA drop-ins against the recorded run of the unmodified reference on
+    examples/sofa_rgbd frames 1-2 (real SIFT keypoints, real depth): RANSAC inlier set identical, homography equal,
+    ICP (partial_set_size 0.7, 100 iterations, 13 k points) within north_star's tolerance."""
+    import warnings
+    from conftest import load_golden
+    from parity import assert_transform_parity
+    q9 = sub("utils.homography_utils.q9")
+    icp = sub("utils.icp")
+    g = load_golden("sofa_pair")
+
+    class KP:
+        def __init__(self, p):
+            self.pt = (float(p[0]), float(p[1]))
+
+    img = np.zeros(tuple(g["img_shape"]), np.uint8)
+    np.random.seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        H, fm = q9.ransac_loop(img, img, [KP(p) for p in g["kp1"]], [KP(p) for p in g["kp2"]], g["bf"])
+    assert np.array_equal(fm, g["matches"]), "RANSAC inlier set differs from the reference's"
+    np.testing.assert_allclose(H, g["H"], rtol=1e-9, atol=1e-12)
+
+    tol, max_it, partial = g["icp_kw"]
+    T, dist, it = icp.icp(g["icp_A"], g["icp_B"], tolerance=float(tol), max_iterations=int(max_it), partial_set_size=float(partial))
+    assert it == int(g["icp_iters"])
+    assert dist.shape == g["icp_dist_sorted"].shape
+    assert_transform_parity(T, g["icp_T"], O.scene_extent(g["icp_B"]), "sofa pair")
+    np.testing.assert_allclose(np.sort(dist), g["icp_dist_sorted"], rtol=0, atol=1e-4 * O.scene_extent(g["icp_B"]))

@@ -149,3 +149,21 @@ def test_chain_prefix():
     Ts = [np.eye(4) + rng.normal(size=(4, 4)) * 0.01 for _ in range(5)]
     P = O.chain_prefix(Ts)
     assert np.allclose(P[3], Ts[3] @ Ts[2] @ Ts[1] @ Ts[0])
+
+
+def test_sofa_pair_reference_run():
+    """The reference's own register_imgs on examples/sofa_rgbd frames 1-2 (tests/golden/make_golden_sofa.py):
+    the oracle must reproduce its RANSAC stage (same seeded draws) and its ICP stage."""
+    import warnings
+    g = load_golden("sofa_pair")
+    np.random.seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        H, fm, counts = O.ransac_loop_pts(tuple(g["img_shape"]), g["kp1"], g["kp2"], g["bf"])
+    assert np.array_equal(fm, g["matches"])
+    np.testing.assert_allclose(H, g["H"], rtol=1e-9, atol=1e-12)
+    tol, max_it, partial = g["icp_kw"]
+    T, dist, it = O.icp(g["icp_A"], g["icp_B"], tolerance=float(tol), max_iterations=int(max_it), partial_set_size=float(partial))
+    assert it == int(g["icp_iters"])
+    np.testing.assert_allclose(T, g["icp_T"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.sort(dist), g["icp_dist_sorted"], rtol=0, atol=1e-7)
