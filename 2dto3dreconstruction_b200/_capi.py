@@ -54,6 +54,9 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_homography_points": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "r3d_ransac3d_score": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "r3d_match_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "r3d_match_descriptors": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_void_p]),
     "r3d_register_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "r3d_register_depth_pairs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_double, c_double,
                                          ctypes.POINTER(IcpParams), c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,0 +1,144 @@
+// K5: brute-force descriptor matching with cross-check -- the step right before
+// RANSAC.  Replaces cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2) as the reference
+// calls it (utils/transformation3d.py:31-32): query i and train j are matched iff j is the nearest train
+// descriptor of i AND i is the nearest query descriptor of j, first minimum (lowest index) on ties in both
+// directions; the distance is sqrt(sum (a-b)^2) in float32.
+//
+// SIFT descriptors are float32 holding integers 0..255, so every squared distance is an integer below 2^24 and
+// exact in float32 whatever the summation order: indices AND distances are bit-identical to OpenCV's.  For
+// general float descriptors the indices agree wherever the minima are not within rounding of each other.
+//
+// Sizes are small (hundreds to a few thousand descriptors of 128 floats, < 1 GFLOP): two launches of a
+// shared-memory tiled argmin kernel (queries->trains and trains->queries) and one cross-check pass.  No tensor
+// cores: the whole problem is a few microseconds of CUDA-core work and has to be exact.
+#include "common.cuh"
+
+namespace r3d {
+
+constexpr int MT_THREADS = 128;
+constexpr int MT_ROWS_PER_WARP = 4;                              // X rows whose minima one warp tracks
+constexpr int MT_X_TILE = (MT_THREADS / 32) * MT_ROWS_PER_WARP;  // 16 X rows per CTA
+constexpr int MT_Y_TILE = 32;                                    // Y rows staged per step
+
+// For every row of X: argmin over the rows of Y of the squared L2 distance (first minimum on ties).
+// blockIdx.y selects the direction: 0: X = A, Y = B; 1: X = B, Y = A.
+__global__ void __launch_bounds__(MT_THREADS)
+bf_argmin_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb, int dim, int dim_pad,
+                 int32_t* __restrict__ idx_ab, float* __restrict__ d2_ab, int32_t* __restrict__ idx_ba,
+                 float* __restrict__ d2_ba) {
+    extern __shared__ float sm[];
+    const bool rev = blockIdx.y == 1;
+    const float* X = rev ? B : A;
+    const float* Y = rev ? A : B;
+    const int nx = rev ? nb : na, ny = rev ? na : nb;
+    int32_t* idx_out = rev ? idx_ba : idx_ab;
+    float* d2_out = rev ? d2_ba : d2_ab;
+    const int x0 = blockIdx.x * MT_X_TILE;
+    if (x0 >= nx) return;
+    float* sX = sm;                                   // [MT_X_TILE][dim_pad]
+    float* sY = sm + (size_t)MT_X_TILE * dim_pad;     // [MT_Y_TILE][dim_pad]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < MT_X_TILE * dim_pad; e += MT_THREADS) {
+        const int r = e / dim_pad, c = e - r * dim_pad;
+        sX[e] = (x0 + r < nx && c < dim) ? X[(size_t)(x0 + r) * dim + c] : 0.0f;
+    }
+    float best[MT_ROWS_PER_WARP];
+    int bidx[MT_ROWS_PER_WARP];
+#pragma unroll
+    for (int k = 0; k < MT_ROWS_PER_WARP; k++) { best[k] = __int_as_float(0x7f800000); bidx[k] = -1; }
+    const float* myX = sX + (size_t)warp * MT_ROWS_PER_WARP * dim_pad;
+    for (int y0 = 0; y0 < ny; y0 += MT_Y_TILE) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < MT_Y_TILE * dim_pad; e += MT_THREADS) {
+            const int r = e / dim_pad, c = e - r * dim_pad;
+            sY[e] = (y0 + r < ny && c < dim) ? Y[(size_t)(y0 + r) * dim + c] : 0.0f;
+        }
+        __syncthreads();
+        const int rows = min(MT_Y_TILE, ny - y0);
+        for (int r = 0; r < rows; r++) {
+            const float* yr = sY + (size_t)r * dim_pad;
+            float acc[MT_ROWS_PER_WARP];
+#pragma unroll
+            for (int k = 0; k < MT_ROWS_PER_WARP; k++) acc[k] = 0.0f;
+            for (int c = lane; c < dim_pad; c += 32) {
+                const float yv = yr[c];
+#pragma unroll
+                for (int k = 0; k < MT_ROWS_PER_WARP; k++) {
+                    const float d = myX[(size_t)k * dim_pad + c] - yv;
+                    acc[k] = fmaf(d, d, acc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < MT_ROWS_PER_WARP; k++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+                if (acc[k] < best[k]) { best[k] = acc[k]; bidx[k] = y0 + r; }      // strict: first minimum wins
+            }
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < MT_ROWS_PER_WARP; k++) {
+            const int x = x0 + warp * MT_ROWS_PER_WARP + k;
+            if (x < nx) { idx_out[x] = bidx[k]; d2_out[x] = best[k]; }
+        }
+    }
+}
+
+__global__ void bf_cross_kernel(const int32_t* __restrict__ idx_ab, const float* __restrict__ d2_ab,
+                                const int32_t* __restrict__ idx_ba, int na, int cross_check,
+                                int32_t* __restrict__ train_out, float* __restrict__ dist_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= na) return;
+    const int j = idx_ab[i];
+    const bool keep = j >= 0 && (!cross_check || idx_ba[j] == i);
+    train_out[i] = keep ? j : -1;
+    dist_out[i] = keep ? sqrtf(d2_ab[i]) : __int_as_float(0x7f800000);
+}
+
+struct MatchWs {
+    int32_t* idx_ab;
+    float* d2_ab;
+    int32_t* idx_ba;
+    float* d2_ba;
+};
+
+static void match_layout(MatchWs& w, Arena& a, int n1, int n2) {
+    w.idx_ab = a.take<int32_t>((size_t)n1);
+    w.d2_ab = a.take<float>((size_t)n1);
+    w.idx_ba = a.take<int32_t>((size_t)n2);
+    w.d2_ba = a.take<float>((size_t)n2);
+}
+
+}  // namespace r3d
+
+using namespace r3d;
+
+extern "C" size_t r3d_match_workspace_bytes(int n1, int n2) {
+    if (n1 <= 0 || n2 <= 0) return 0;
+    MatchWs w;
+    Arena a(nullptr, 0);
+    match_layout(w, a, n1, n2);
+    return a.used + 512;
+}
+
+extern "C" int r3d_match_descriptors(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
+                                     int32_t* train_idx_out, float* dist_out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (!des1 || !des2 || !train_idx_out || !dist_out || n1 <= 0 || n2 <= 0 || dim <= 0) return R3D_ERR_INVALID;
+    const int dim_pad = (dim + 31) / 32 * 32;
+    const size_t smem = (size_t)(MT_X_TILE + MT_Y_TILE) * dim_pad * sizeof(float);
+    if (smem > 200 * 1024) return R3D_ERR_INVALID;      // descriptors longer than ~1000 floats are not supported
+    cudaStream_t st = (cudaStream_t)stream;
+    MatchWs w;
+    Arena a(workspace, workspace_bytes);
+    match_layout(w, a, n1, n2);
+    if (!a.ok) return R3D_ERR_WORKSPACE;
+    if (smem > 48 * 1024) R3D_CUDA(cudaFuncSetAttribute(bf_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nmax = n1 > n2 ? n1 : n2;
+    R3D_LAUNCH(bf_argmin_kernel, dim3((nmax + MT_X_TILE - 1) / MT_X_TILE, 2), MT_THREADS, smem, st, des1, n1, des2, n2, dim,
+               dim_pad, w.idx_ab, w.d2_ab, w.idx_ba, w.d2_ba);
+    R3D_LAUNCH(bf_cross_kernel, (n1 + 255) / 256, 256, 0, st, w.idx_ab, w.d2_ab, w.idx_ba, n1, cross_check, train_idx_out,
+               dist_out);
+    return R3D_OK;
+}

@@ -190,3 +190,23 @@ def ransac3d_score(T, P, Q, thresh=10.0):
     C.check(C.lib().r3d_ransac3d_score(C.ptr(T), n_hyp, C.ptr(P), C.ptr(Q), P.shape[0], float(thresh), C.ptr(counts),
                                        C.stream_ptr()), "r3d_ransac3d_score")
     return counts
+
+
+def match_descriptors(des1, des2, cross_check=True):
+    """K5: brute-force L2 matching of float32 descriptor sets (CUDA tensors [n1,dim], [n2,dim]).
+    Returns (train_idx int32 [n1] with -1 for unmatched queries, dist float32 [n1])."""
+    C.require_device()
+    t = C.torch()
+    des1 = des1.contiguous()
+    des2 = des2.contiguous()
+    assert des1.dtype == t.float32 and des2.dtype == t.float32 and des1.dim() == 2 and des2.dim() == 2
+    assert des1.shape[1] == des2.shape[1]
+    n1, n2, dim = des1.shape[0], des2.shape[0], des1.shape[1]
+    train = t.empty(n1, dtype=t.int32, device="cuda")
+    dist = t.empty(n1, dtype=t.float32, device="cuda")
+    L = C.lib()
+    nws = L.r3d_match_workspace_bytes(n1, n2)
+    ws = C.workspace(nws)
+    C.check(L.r3d_match_descriptors(C.ptr(des1), n1, C.ptr(des2), n2, dim, 1 if cross_check else 0, C.ptr(train), C.ptr(dist),
+                                    C.ptr(ws), nws, C.stream_ptr()), "r3d_match_descriptors")
+    return train, dist

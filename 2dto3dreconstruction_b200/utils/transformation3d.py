@@ -7,7 +7,8 @@
 
 register_imgs keeps the reference's control flow, its global-RNG consumption (two np.random.choice
 calls, in the same order) and its quirks (pixel-space keypoints, h.t composition order); only the
-arithmetic moved to the device.  SIFT + brute-force matching stay on OpenCV (out of scope, N1).
+arithmetic moved to the device.  SIFT detection stays on OpenCV (out of scope); the brute-force
+cross-checked descriptor matching that follows it runs in the K5 kernel (csrc/match.cu).
 """
 import numpy as np
 
@@ -45,15 +46,36 @@ def get_transformed_points(points, h):
     return ops.transform_points(pts, T).cpu().numpy()
 
 
+class DMatch:
+    """The three fields of cv2.DMatch the reference reads (utils/transformation3d.py:40, :254)."""
+    __slots__ = ("queryIdx", "trainIdx", "distance", "imgIdx")
+
+    def __init__(self, q, t, d):
+        self.queryIdx, self.trainIdx, self.distance, self.imgIdx = int(q), int(t), float(d), 0
+
+
+def match_descriptors(des1, des2):
+    """cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2) (utils/transformation3d.py:31-32):
+    mutual nearest neighbours in L2, first minimum on ties, ordered by query index."""
+    d1 = np.ascontiguousarray(des1, dtype=np.float32)
+    d2 = np.ascontiguousarray(des2, dtype=np.float32)
+    if d1.ndim != 2 or d2.ndim != 2 or d1.shape[1] != d2.shape[1]:
+        raise ValueError("expected two (n, dim) descriptor arrays of equal dim")
+    if d1.shape[0] == 0 or d2.shape[0] == 0:
+        return []
+    train, dist = ops.match_descriptors(C.to_device(d1), C.to_device(d2), cross_check=True)
+    train, dist = train.cpu().numpy(), dist.cpu().numpy()
+    return [DMatch(i, train[i], dist[i]) for i in np.nonzero(train >= 0)[0]]
+
+
 def generate_keypoints_and_match(img1, img2):
-    """SIFT keypoints + cross-checked brute-force matches via OpenCV
-    (utils/transformation3d.py:15-34).  Feature front-end: not part of the accelerated path."""
+    """SIFT keypoints (OpenCV; detection is outside the accelerated path) + cross-checked brute-force
+    matches on the device (utils/transformation3d.py:15-34)."""
     import cv2
     sift = cv2.xfeatures2d.SIFT_create() if hasattr(cv2, "xfeatures2d") else cv2.SIFT_create()
     kp1, des1 = sift.detectAndCompute(img1, mask=None)
     kp2, des2 = sift.detectAndCompute(img2, mask=None)
-    matcher = cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True)
-    return kp1, kp2, matcher.match(des1, des2)
+    return kp1, kp2, match_descriptors(des1, des2)
 
 
 def get_key_points_from_matches(kp1, kp2, matches):

@@ -175,6 +175,19 @@ int r3d_ransac3d_score(const double* T, int n_hyp, const double* P, const double
                        double thresh, int32_t* counts_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K5  brute-force descriptor matching with cross-check (the step before RANSAC)
+ *   replaces cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2) as called at
+ *   utils/transformation3d.py:31-32 (OpenCV is a third-party dependency of the reference, not vendored).
+ *   des1: [n1, dim] float32 query descriptors, des2: [n2, dim] float32 train descriptors.
+ *   train_idx_out int32[n1]: the matched train index of every query, or -1 (cross_check != 0: kept only when
+ *   the two are each other's nearest, first minimum on ties); dist_out float32[n1]: L2 distance (inf if none).
+ * ------------------------------------------------------------------------------------ */
+size_t r3d_match_workspace_bytes(int n1, int n2);
+int r3d_match_descriptors(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
+                          int32_t* train_idx_out, float* dist_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Fused registration of depth-frame pairs: K1 on both frames, grid build, ICP.
  *   The batched form of the reference's pair loop body (reconstruct.py:319-324 /
  *   reconstruct_rgbd.py:48) for the synthetic-depth configuration.

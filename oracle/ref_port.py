@@ -442,6 +442,31 @@ def affine_hypotheses(P, Q, samples):
 
 
 # --------------------------------------------------------------------------------------
+# K5: cross-checked brute-force descriptor matching.
+# The reference calls cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2)
+# (utils/transformation3d.py:31-32); OpenCV is a third-party dependency (opencv-contrib-python 3.4.2.16,
+# requirements.txt:59) that is not vendored under /root/reference.  Its published behaviour, restated: a
+# query i and a train j are matched iff j = argmin_j |d1_i - d2_j| and i = argmin_i |d1_i - d2_j| (first
+# minimum on ties), the distance is the float32 L2 norm, and the matches come ordered by query index.
+# Pinned against the OpenCV in this image (4.13) by tests/test_oracle_golden.py::test_match_descriptors_vs_cv2;
+# releases before 3.4.9 / 4.2 applied a weaker, one-directional cross-check.
+# --------------------------------------------------------------------------------------
+
+def match_descriptors(des1, des2):
+    """Returns (query_idx int64 [K], train_idx int64 [K], dist float32 [K])."""
+    d1 = np.asarray(des1, dtype=np.float32)
+    d2 = np.asarray(des2, dtype=np.float32)
+    D2 = np.empty((d1.shape[0], d2.shape[0]), dtype=np.float32)
+    for s in range(0, d1.shape[0], 256):
+        diff = d1[s:s + 256, None, :] - d2[None, :, :]
+        D2[s:s + 256] = (diff * diff).sum(axis=2, dtype=np.float32)
+    q2t = D2.argmin(axis=1)
+    t2q = D2.argmin(axis=0)
+    q = np.nonzero(t2q[q2t] == np.arange(d1.shape[0]))[0]
+    return q, q2t[q], np.sqrt(D2[q, q2t[q]]).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
 # Chaining prefix product  (reconstruct.py:201-204)
 # --------------------------------------------------------------------------------------
 

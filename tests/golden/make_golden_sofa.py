@@ -51,6 +51,16 @@ def main():
         rec["icp_T"], rec["icp_dist_sorted"], rec["icp_iters"] = np.array(T), np.sort(d), np.array(it)
         return T, d, it
 
+    # the descriptor matching stage (utils/transformation3d.py:27-32): same SIFT call, descriptors recorded
+    sift = cv2.xfeatures2d.SIFT_create()
+    _, des1 = sift.detectAndCompute(rgb[1], mask=None)
+    _, des2 = sift.detectAndCompute(rgb[0], mask=None)
+    assert np.array_equal(des1, np.rint(des1)) and des1.min() >= 0 and des1.max() <= 255      # integer-valued float32
+    bf = cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2)
+    rec["des1"], rec["des2"] = des1.astype(np.uint8), des2.astype(np.uint8)
+    rec["bf_dist"] = np.array([m.distance for m in bf], dtype=np.float32)
+    bf_pairs = np.array([(m.queryIdx, m.trainIdx) for m in bf])
+
     t3d.ransac_loop, t3d.icp = ransac_spy, icp_spy
     np.random.seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
@@ -59,6 +69,7 @@ def main():
                                     filter_pts_frac=0.05, partial_set_frac=0.7)
     t3d.ransac_loop, t3d.icp = real_ransac, real_icp
     rec.pop("rng_before_ransac")
+    assert np.array_equal(rec["bf"], bf_pairs), "register_imgs matched other descriptors than the recorded ones"
     # the 3-D keypoint triples and the affine fit between the two stages (utils/transformation3d.py:261-275)
     save("sofa_pair", final_h=np.array(h), n_cloud=np.array([c.shape[0] for c in clouds]), **rec)
     print({k: getattr(v, "shape", v) for k, v in rec.items()})

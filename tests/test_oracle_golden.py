@@ -167,3 +167,26 @@ def test_sofa_pair_reference_run():
     assert it == int(g["icp_iters"])
     np.testing.assert_allclose(T, g["icp_T"], rtol=0, atol=1e-9)
     np.testing.assert_allclose(np.sort(dist), g["icp_dist_sorted"], rtol=0, atol=1e-7)
+
+
+def test_match_descriptors_vs_cv2():
+    """K5 oracle: the recorded cv2.BFMatcher(crossCheck=True) output of the reference run on the sofa frames, and
+    OpenCV itself (a third-party dependency of the reference, present in this image) on random sets with ties."""
+    g = load_golden("sofa_pair")
+    q, t, d = O.match_descriptors(g["des1"].astype(np.float32), g["des2"].astype(np.float32))
+    assert np.array_equal(np.stack((q, t), axis=1), g["bf"])
+    assert np.array_equal(d, g["bf_dist"])
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(4)
+    for trial in range(4):
+        n1, n2 = rng.integers(20, 300, 2)
+        d1 = rng.integers(0, 256, (n1, 128)).astype(np.float32)
+        d2 = rng.integers(0, 256, (n2, 128)).astype(np.float32)
+        if trial >= 2:      # duplicates and low-entropy descriptors: exact ties in both directions
+            d2[: n2 // 3] = d1[rng.integers(0, n1, n2 // 3)]
+            d1[:, 6:] = 0
+            d2[:, 6:] = 0
+        m = cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(d1, d2)
+        q, t, d = O.match_descriptors(d1, d2)
+        assert np.array_equal(np.stack((q, t), axis=1), np.array([(x.queryIdx, x.trainIdx) for x in m]).reshape(-1, 2))
+        assert np.array_equal(d, np.array([x.distance for x in m], dtype=np.float32))
