@@ -84,6 +84,13 @@ __device__ __forceinline__ void store_point(Point4* p, double x, double y, doubl
     q[1] = make_double2(z, __longlong_as_double((long long)(uint32_t)idx));
 }
 
+// tag = cloud index (low word) | a second index (high word); load_point / consider() read the low word only
+__device__ __forceinline__ void store_point_tagged(Point4* p, double x, double y, double z, int32_t idx, int32_t hi) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(x, y);
+    q[1] = make_double2(z, __hiloint2double(hi, idx));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -278,7 +278,9 @@ gather_kernel(GridWorkspace w, const Point4* __restrict__ dst, const int32_t* __
         if (i < g.n_pts) {
             const uint32_t v = vals[i];
             Point4 p = load_point(src + v);
-            store_point(out + i, p.x, p.y, p.z, (int32_t)v);
+            // high word of the tag = the point's own sorted position: a raw copy of the record (TMA staging in
+            // lean_search.cuh) then carries everything the search needs
+            store_point_tagged(out + i, p.x, p.y, p.z, (int32_t)v, (int32_t)i);
             const uint32_t k = keys[i];
             starts += (i == 0) || ((keys[i - 1] >> 6) != (k >> 6));
         }

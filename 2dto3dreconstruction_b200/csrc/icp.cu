@@ -398,6 +398,29 @@ __device__ __forceinline__ double warp_reduce16(const double (&m)[16], double* s
     return s;      // lanes 0..15 hold the sum of moment `lane`
 }
 
+// Same sums in two passes of eight moments, with half the scratch (8 * 33 doubles per warp).
+__device__ __forceinline__ double warp_reduce16_small(const double (&m)[16], double* scratch) {
+    const int lane = threadIdx.x & 31;
+    const int row = lane & 7, quarter = lane >> 3;
+    double result = 0.0;
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; k++) scratch[k * 33 + lane] = m[pass * 8 + k];
+        __syncwarp();
+        const double* r = scratch + row * 33 + quarter * 8;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += r[j];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if (quarter == pass) result = s;      // lanes 0..7: moments 0..7; lanes 8..15: moments 8..15
+    }
+    __syncwarp();
+    return result;      // lanes 0..15 hold the sum of moment `lane`
+}
+
 __device__ __forceinline__ void warp_reduce16_store(const double (&m)[16], double* scratch, double* __restrict__ out16) {
     const double s = warp_reduce16(m, scratch);
     if ((threadIdx.x & 31) < 16) out16[threadIdx.x & 31] = s;
@@ -533,9 +556,9 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     __shared__ GridParams g;
     __shared__ double T[12], D[12];
     __shared__ int s_n, s_done;
-    __shared__ __align__(16) double scratch[NN_THREADS / 32][16 * 33];     // moment reduction scratch
+    __shared__ __align__(16) double scratch[NN_THREADS / 32][8 * 33];      // moment reduction scratch (two passes of 8)
     // survivors list of each warp; never shared with the reduction: its stale slots must stay real points
-    __shared__ double2 lists[NN_THREADS / 32][2 * LEAN_LIST_CAP];
+    __shared__ double2 lists[NN_THREADS / 32][LEAN_WARP_SMEM];
     if (threadIdx.x == 0) {
         g = w.grid.params[pair];
         s_n = w.state[pair].n_src;
@@ -557,6 +580,15 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
     list_init(lists[warp], v.pts);
+    unsigned tma_phase = 0;      // parities of the warp's two staging mbarriers (lean_search.cuh)
+#if R3D_LEAN_TMA
+    if (lane == 0) {
+        mbar_init(smem_u32(lists[warp] + 2 * LEAN_LIST_CAP + 128), 1);
+        mbar_init(smem_u32(lists[warp] + 2 * LEAN_LIST_CAP + 128) + 8u, 1);
+    }
+    mbar_init_fence();
+    __syncwarp();
+#endif
     while (true) {
         int vw = 0;
         if (lane == 0) vw = atomicAdd(vw_counter, 1);
@@ -592,7 +624,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             }
             R3D_STAT(0, 1);
             float cover = 0.0f;
-            lean_search(lists[warp], seed, other, v, g, active && !skip, qx, qy, qz, slack, cover);
+            lean_search(lists[warp], tma_phase, seed, other, v, g, active && !skip, qx, qy, qz, slack, cover);
             const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
 #ifdef R3D_NN_STATS
             R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip)));
@@ -623,7 +655,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
                                     b.z - g.shift[2], sqrt(best.d2));
                 }
-                acc += warp_reduce16(m, scratch[warp]);
+                acc += warp_reduce16_small(m, scratch[warp]);
             }
         }
         if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;

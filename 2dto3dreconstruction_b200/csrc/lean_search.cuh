@@ -26,6 +26,16 @@
 #pragma once
 #include "coop_search.cuh"
 
+// Candidate stream staged into shared memory by cp.async.bulk (1) or by per-lane LDG (0).  The TMA path is
+// correct and tested (build with R3D_LEAN_TMA=1) but measured 15% slower, 333 vs 289 us per launch
+// (profiles/r01_nn_sweeps.md, sweep_12): a segment is ~5 points (160 B), every copy has its own source,
+// destination and size, and UBLKCP takes them from uniform registers, so the ~30 copies of a task are issued
+// one lane at a time (ELECT + 5 R2UR + UBLKCP + branch each) -- more instructions than the binary search and
+// the two coalesced LDG.128 per lane they replace, in a kernel that is issue bound.
+#ifndef R3D_LEAN_TMA
+#define R3D_LEAN_TMA 0
+#endif
+
 namespace r3d {
 
 constexpr int LEAN_SEG_CAP = 2048;     // segments per round the warp walk accepts
@@ -34,6 +44,9 @@ constexpr int LEAN_LIST_CAP = 64;      // survivors list: at most LEAN_FLUSH - 1
 #define R3D_LEAN_FLUSH 24
 #endif
 constexpr int LEAN_FLUSH = R3D_LEAN_FLUSH;      // scan the list as soon as it holds this many points (<= 32)
+// shared memory of one warp, in double2: survivor list (xy + zw), and with TMA staging two buffers of 32 raw
+// records plus their two mbarriers
+constexpr int LEAN_WARP_SMEM = 2 * LEAN_LIST_CAP + (R3D_LEAN_TMA ? 128 + 2 : 0);
 #ifndef R3D_FULL_MASK_DEFINED
 #define R3D_FULL_MASK_DEFINED
 constexpr unsigned FULL = 0xffffffffu;
@@ -78,7 +91,49 @@ struct WarpList {
     double2* szw;      // [LEAN_LIST_CAP] (z, tag)
     int n;             // warp-uniform
     double lo[3], hi[3];      // filter box (world coordinates)
+#if R3D_LEAN_TMA
+    const double2* stage;     // two staging buffers of 32 raw 32-byte records each, filled by cp.async.bulk
+    uint32_t stage_addr;      // shared-window address of `stage`
+    uint32_t mbar0;           // shared-window address of buffer 0's mbarrier; buffer 1's is 8 bytes further
+    unsigned phase;           // bit b: parity the next wait on mbarrier b uses
+#endif
 };
+
+#if R3D_LEAN_TMA
+// ---- TMA (bulk async copy) plumbing: 1-D cp.async.bulk global -> shared, completion on an mbarrier ---------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        asm volatile(
+            "{\n"
+            " .reg .pred p;\n"
+            " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            " selp.u32 %0, 1, 0, p;\n"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    __trap();      // a lost byte count would otherwise hang the GPU
+}
+#endif
 
 // Every lane scans the list, four entries at a time.  Slots past n hold points of earlier batches (or
 // the point the list was initialised with): real points of the same cloud, harmless to re-evaluate.
@@ -104,8 +159,7 @@ __device__ __forceinline__ void list_init(double2* list, const Point4* __restric
     const int lane = threadIdx.x & 31;
     const double2* p = reinterpret_cast<const double2*>(pts);
     const double2 xy = __ldg(p);
-    double2 zw = __ldg(p + 1);
-    zw.y = __hiloint2double(0, __double2loint(zw.y));
+    const double2 zw = __ldg(p + 1);      // the tag carries the cloud index and the sorted position (0)
 #pragma unroll
     for (int k = lane; k < LEAN_LIST_CAP; k += 32) {
         list[k] = xy;
@@ -161,6 +215,42 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
         if (total == 0u) continue;
         double2 xy = make_double2(0.0, 0.0), zw = make_double2(0.0, 0.0);
         bool have = false;
+#if R3D_LEAN_TMA
+        // The stream is staged 32 records at a time into one of two shared-memory buffers by bulk async copies:
+        // the lane that owns a segment copies the part of it that falls into the chunk's window straight to its
+        // place in the buffer (the prefix sums are the compaction), lane 0 announces the chunk's byte count to
+        // the buffer's mbarrier, and the next chunk is in flight while the current one is filtered and scanned.
+        const uint32_t nchunks = (total + 31u) >> 5;
+        auto issue = [&](uint32_t c) {
+            const uint32_t c0 = c << 5, b = c & 1u;
+            if (lane == 0) mbar_arrive_expect_tx(L.mbar0 + 8u * b, min(32u, total - c0) * 32u);
+            const uint32_t lo = max(excl, c0), hi = min(excl + cnt, c0 + 32u);
+            if (hi > lo) bulk_copy_g2s(L.stage_addr + (b * 32u + (lo - c0)) * 32u, v.pts + s + (lo - excl), (hi - lo) * 32u, L.mbar0 + 8u * b);
+        };
+        issue(0u);
+        for (uint32_t c = 0; c < nchunks; c++) {
+            if (c + 1u < nchunks) issue(c + 1u);      // its buffer was last read two chunks ago, before a __syncwarp
+            const uint32_t b = c & 1u;
+            mbar_wait(L.mbar0 + 8u * b, (L.phase >> b) & 1u);
+            L.phase ^= 1u << b;
+            have = (c << 5) + (uint32_t)lane < total;
+            if (have) {
+                xy = L.stage[(b * 32u + lane) * 2u];
+                zw = L.stage[(b * 32u + lane) * 2u + 1u];
+            }
+            __syncwarp();      // every lane has its record: the buffer may be refilled
+            const bool keep = have && xy.x >= L.lo[0] && xy.x <= L.hi[0] && xy.y >= L.lo[1] && xy.y <= L.hi[1] &&
+                              zw.x >= L.lo[2] && zw.x <= L.hi[2];
+            const unsigned bal = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int slot = L.n + __popc(bal & lt);
+                L.sxy[slot] = xy;
+                L.szw[slot] = zw;
+            }
+            L.n += __popc(bal);
+            if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
+        }
+#else
         // resolve stream index t = t0 + lane and issue its loads
         auto fetch = [&](uint32_t t0) {
             const uint32_t t = t0 + (uint32_t)lane;
@@ -177,7 +267,6 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 const double2* p = reinterpret_cast<const double2*>(v.pts + pos);
                 xy = __ldg(p);
                 zw = __ldg(p + 1);
-                zw.y = __hiloint2double((int)pos, __double2loint(zw.y));
             }
         };
         fetch(0u);
@@ -194,6 +283,7 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
             if (t0 + 32 < total) fetch(t0 + 32);          // next batch's loads fly while the list is scanned
             if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
         }
+#endif
     }
     if (L.n > 0) list_flush(L, best, seed_pos, qx, qy, qz);
 }
@@ -232,8 +322,9 @@ __device__ __forceinline__ float wmax_f(float v) { return sord2f(__reduce_max_sy
 __device__ __forceinline__ int cell_lo(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 
-__device__ __forceinline__ void lean_search(double2* list, const Best& seed, Best& other, const GridView& v, const GridParams& g,
-                                            bool active, double qx, double qy, double qz, float slack, float& cover) {
+__device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, const Best& seed, Best& other, const GridView& v,
+                                            const GridParams& g, bool active, double qx, double qy, double qz, float slack,
+                                            float& cover) {
     // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
     // margin: 2e-3 cells absolute plus 2.4e-7 relative to the coordinate (one float ulp), on top of the
     // 1e-6 relative slack of the radius.
@@ -251,6 +342,12 @@ __device__ __forceinline__ void lean_search(double2* list, const Best& seed, Bes
     L.sxy = list;
     L.szw = list + LEAN_LIST_CAP;
     L.n = 0;
+#if R3D_LEAN_TMA
+    L.stage = list + 2 * LEAN_LIST_CAP;
+    L.stage_addr = smem_u32(L.stage);
+    L.mbar0 = smem_u32(list + 2 * LEAN_LIST_CAP + 128);
+    L.phase = tma_phase;
+#endif
 #ifndef R3D_LEAN_RCAP0
 #define R3D_LEAN_RCAP0 1.0f
 #endif
@@ -259,7 +356,12 @@ __device__ __forceinline__ void lean_search(double2* list, const Best& seed, Bes
     cover = 0.0f;
     while (true) {
         const unsigned unfin = __ballot_sync(FULL, !fin);
-        if (unfin == 0u) return;
+        if (unfin == 0u) {
+#if R3D_LEAN_TMA
+            tma_phase = L.phase;
+#endif
+            return;
+        }
         R3D_STAT(1, 1);
         const int leader = __ffs(unfin) - 1;
         // float sqrt rounded up
