@@ -239,40 +239,72 @@ r2_score_kernel(const double* __restrict__ Hre, const double* __restrict__ Him, 
 }
 
 // ---- K4B -----------------------------------------------------------------------------------------
-// One hypothesis per lane; the CTA stages a tile of correspondences in shared memory and every lane
-// streams it with broadcast reads, so a point costs two LDS per warp for 32 evaluations.  grid.y
-// splits the correspondences; per-hypothesis partial counts are combined with atomicAdd.
+// One hypothesis per lane.  The CTA streams tiles of correspondences through shared memory and every lane
+// reads them by broadcast, so a correspondence costs four LDS per warp for 32 evaluations.  The tiles are
+// staged by TMA: one thread issues two bulk async copies per tile (the P and Q records are contiguous,
+// 8 KB each) into one of two buffers and the copy of the next tile runs while the current one is scored.
+// grid.y splits the correspondences; per-hypothesis partial counts are combined with atomicAdd.
+#ifndef R3D_RS3_TILE
+#define R3D_RS3_TILE 64
+#endif
+#ifndef R3D_RS3_MINB
+#define R3D_RS3_MINB 8
+#endif
 constexpr int RS3_THREADS = 128;
-constexpr int RS3_TILE = 512;    // points staged per step: 512 * 48 B = 24 KB
+constexpr int RS3_TILE = R3D_RS3_TILE;    // correspondences per stage: 2 x 64 x 32 B = 4 KB, two stages (measured best of 64..512)
 
-__global__ void __launch_bounds__(RS3_THREADS)
+__global__ void __launch_bounds__(RS3_THREADS, R3D_RS3_MINB)
 r3_score_kernel(const double* __restrict__ T, int n_hyp, const Point4* __restrict__ P, const Point4* __restrict__ Q,
                 int n_pts, int pts_per_cta, double thresh, int32_t* __restrict__ counts) {
-    __shared__ double sp[RS3_TILE][6];
+    __shared__ __align__(128) double2 sP[2][RS3_TILE * 2];     // raw 32-byte records: (x, y), (z, tag)
+    __shared__ __align__(128) double2 sQ[2][RS3_TILE * 2];
+    __shared__ __align__(8) unsigned long long bars[2];
     const int hyp = blockIdx.x * RS3_THREADS + threadIdx.x;
     double t[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) t[k] = (hyp < n_hyp) ? T[(size_t)hyp * 16 + k] : 0.0;
     const int p0 = blockIdx.y * pts_per_cta, p1 = min(n_pts, p0 + pts_per_cta);
+    const int tiles = (p1 - p0 + RS3_TILE - 1) / RS3_TILE;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+    }
+    mbar_init_fence();
+    __syncthreads();
+    auto issue = [&](int tile) {      // thread 0 only
+        const int base = p0 + tile * RS3_TILE, m = min(RS3_TILE, p1 - base), b = tile & 1;
+        mbar_arrive_expect_tx(bar0 + 8u * b, 2u * (uint32_t)m * 32u);
+        bulk_copy_g2s(smem_u32(sP[b]), P + base, (uint32_t)m * 32u, bar0 + 8u * b);
+        bulk_copy_g2s(smem_u32(sQ[b]), Q + base, (uint32_t)m * 32u, bar0 + 8u * b);
+    };
+    if (threadIdx.x == 0 && tiles > 0) issue(0);
     int cnt = 0;
-    for (int base = p0; base < p1; base += RS3_TILE) {
-        const int m = min(RS3_TILE, p1 - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < m; k += RS3_THREADS) {
-            const Point4 a = load_point(P + base + k), b = load_point(Q + base + k);
-            sp[k][0] = a.x; sp[k][1] = a.y; sp[k][2] = a.z;
-            sp[k][3] = b.x; sp[k][4] = b.y; sp[k][5] = b.z;
-        }
-        __syncthreads();
+    unsigned phase = 0;
+    for (int tile = 0; tile < tiles; tile++) {
+        const int b = tile & 1;
+        // buffer b ^ 1 was last read in tile - 1, and every thread has passed the barrier that ended it
+        if (threadIdx.x == 0 && tile + 1 < tiles) issue(tile + 1);
+        mbar_wait(bar0 + 8u * b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const int m = min(RS3_TILE, p1 - (p0 + tile * RS3_TILE));
+        const double2* sp = sP[b];
+        const double2* sq = sQ[b];
 #pragma unroll 4
         for (int k = 0; k < m; k++) {
-            const double x = sp[k][0], y = sp[k][1], z = sp[k][2];
-            const double dx = (((t[0] * x + t[1] * y) + t[2] * z) + t[3]) - sp[k][3];
-            const double dy = (((t[4] * x + t[5] * y) + t[6] * z) + t[7]) - sp[k][4];
-            const double dz = (((t[8] * x + t[9] * y) + t[10] * z) + t[11]) - sp[k][5];
+            const double2 pxy = sp[2 * k];
+            const double pz = sp[2 * k + 1].x;
+            const double2 qxy = sq[2 * k];
+            const double qz = sq[2 * k + 1].x;
+            // three fused multiply-adds per coordinate, the translation as the innermost addend (16 fp64
+            // instructions per evaluation instead of 19); differs from an unfused left-to-right sum by rounding only
+            const double dx = fma(t[0], pxy.x, fma(t[1], pxy.y, fma(t[2], pz, t[3]))) - qxy.x;
+            const double dy = fma(t[4], pxy.x, fma(t[5], pxy.y, fma(t[6], pz, t[7]))) - qxy.y;
+            const double dz = fma(t[8], pxy.x, fma(t[9], pxy.y, fma(t[10], pz, t[11]))) - qz;
             const double r2 = dx * dx + dy * dy + dz * dz;
             cnt += (r2 < thresh);
         }
+        __syncthreads();      // the buffer may be refilled
     }
     if (hyp < n_hyp && cnt) atomicAdd(counts + hyp, cnt);
 }
@@ -316,11 +348,22 @@ extern "C" int r3d_ransac3d_score(const double* T, int n_hyp, const double* P, c
     R3D_CUDA(cudaMemsetAsync(counts_out, 0, (size_t)n_hyp * sizeof(int32_t), st));
     if (n_pts == 0) return R3D_OK;
     const int gx = (n_hyp + RS3_THREADS - 1) / RS3_THREADS;
-    // enough CTAs for ~4 waves of 148 SMs x 8 resident CTAs
-    int gy = (148 * 8 * 4 + gx - 1) / gx;
+    // split the correspondences so that the grid is close to a whole number of waves of 148 SMs x resident CTAs
+    int resident = 0;
+    R3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, r3_score_kernel, RS3_THREADS, 0));
+    if (resident < 1) resident = 1;
+    const int slots = 148 * resident;
     const int max_gy = (n_pts + RS3_TILE - 1) / RS3_TILE;
-    if (gy > max_gy) gy = max_gy;
-    if (gy < 1) gy = 1;
+    int gy = 1;
+    double best_eff = 0.0;
+    for (int cand = 1; cand <= max_gy && cand <= 64; cand++) {
+        const long long ctas = (long long)gx * cand;
+        const long long waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / (double)(waves * slots);
+        // prefer at least ~3 waves (load balance between CTAs that share an SM), then the fullest last wave
+        if ((waves >= 3 || cand == max_gy) && eff > best_eff + 1e-9) { best_eff = eff; gy = cand; }
+        if (waves >= 8) break;
+    }
     int per = (n_pts + gy - 1) / gy;
     per = (per + RS3_TILE - 1) / RS3_TILE * RS3_TILE;
     gy = (n_pts + per - 1) / per;
