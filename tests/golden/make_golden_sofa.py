@@ -72,6 +72,9 @@ def main():
     assert np.array_equal(rec["bf"], bf_pairs), "register_imgs matched other descriptors than the recorded ones"
     # the 3-D keypoint triples and the affine fit between the two stages (utils/transformation3d.py:261-275)
     save("sofa_pair", final_h=np.array(h), n_cloud=np.array([c.shape[0] for c in clouds]), **rec)
+    # the frames themselves (greyscale as utils/rgbd.py:31 reads them, 16-bit depth), as arrays: inputs of the
+    # end-to-end drop-in test of register_imgs
+    save("sofa_frames", gray=np.stack(rgb), depth=np.stack(depth))
     print({k: getattr(v, "shape", v) for k, v in rec.items()})
     print("iters", rec["icp_iters"], "matches", rec["matches"].shape)
 

@@ -115,3 +115,37 @@ def test_sofa_pair_against_the_reference_run():
     assert dist.shape == g["icp_dist_sorted"].shape
     assert_transform_parity(T, g["icp_T"], O.scene_extent(g["icp_B"]), "sofa pair")
     np.testing.assert_allclose(np.sort(dist), g["icp_dist_sorted"], rtol=0, atol=1e-4 * O.scene_extent(g["icp_B"]))
+
+
+def test_register_imgs_end_to_end_on_the_sofa_frames():
+    """The whole drop-in chain on real frames -- cv2 SIFT, K5 matching, K4A RANSAC, K3c affine fit, transform, ICP
+    (K2 + K3) and the reference's h.t composition -- against the 4x4 the unmodified reference's register_imgs
+    returned for the same call (tests/golden/make_golden_sofa.py), same global-RNG seed."""
+    import time
+    import warnings
+    pytest.importorskip("cv2")
+    from conftest import load_golden
+    t3d = sub("utils.transformation3d")
+    utils = sub("utils.utils")
+    g = load_golden("sofa_pair")
+    f = load_golden("sofa_frames")
+    gray, depth = f["gray"], f["depth"]
+    clouds = [utils.depth_to_voxel_ld(d) for d in depth]
+    assert [c.shape[0] for c in clouds] == list(g["n_cloud"])
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p1, p2, h = t3d.register_imgs(gray[1], gray[0], depth[1], depth[0], img1_pts=clouds[1], img2_pts=clouds[0],
+                                      filter_pts_frac=0.05, partial_set_frac=0.7)
+    print("register_imgs (sofa frames 2 -> 1): %.3f s" % (time.perf_counter() - t0))
+    assert p1 is clouds[1] and p2 is clouds[0]
+    assert_transform_parity(h, g["final_h"], O.scene_extent(clouds[0]), "register_imgs")
+    # the RNG was consumed exactly as the reference consumes it (100 x randint(4) + two choice() calls)
+    after = np.random.randint(1 << 30)
+    np.random.seed(0)
+    for _ in range(100):
+        np.random.randint(len(g["bf"]), size=4)
+    np.random.choice(clouds[1].shape[0], int(clouds[1].shape[0] * 0.05), replace=False)
+    np.random.choice(clouds[0].shape[0], int(clouds[0].shape[0] * 0.05), replace=False)
+    assert after == np.random.randint(1 << 30)
