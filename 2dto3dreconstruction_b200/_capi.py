@@ -54,6 +54,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_homography_points": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "r3d_ransac3d_score": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "r3d_rigid_hypotheses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "r3d_affine_hypotheses": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "r3d_match_workspace_bytes": (c_size_t, [c_int, c_int]),
     "r3d_match_descriptors": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),

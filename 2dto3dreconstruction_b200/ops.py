@@ -210,3 +210,21 @@ def match_descriptors(des1, des2, cross_check=True):
     C.check(L.r3d_match_descriptors(C.ptr(des1), n1, C.ptr(des2), n2, dim, 1 if cross_check else 0, C.ptr(train), C.ptr(dist),
                                     C.ptr(ws), nws, C.stream_ptr()), "r3d_match_descriptors")
     return train, dist
+
+
+def hypotheses_3d(P, Q, samples, kind="rigid"):
+    """K6: one 4x4 hypothesis per minimal sample.  P, Q: CUDA xyzw float64 (n,4); samples: CUDA int32 [n_hyp, 3]
+    (kind 'rigid', utils/r3d.py:22-60 on the sample) or [n_hyp, 4] (kind 'affine',
+    utils/transformation3d.py:163-180 on the sample).  Returns (T [n_hyp,4,4] float64, status int32 [n_hyp])."""
+    C.require_device()
+    t = C.torch()
+    samples = samples.contiguous()
+    k = 3 if kind == "rigid" else 4
+    assert samples.dtype == t.int32 and samples.dim() == 2 and samples.shape[1] == k
+    n_hyp = samples.shape[0]
+    T = t.empty((n_hyp, 4, 4), dtype=t.float64, device="cuda")
+    status = t.empty(n_hyp, dtype=t.int32, device="cuda")
+    fn = C.lib().r3d_rigid_hypotheses if kind == "rigid" else C.lib().r3d_affine_hypotheses
+    C.check(fn(C.ptr(P), C.ptr(Q), P.shape[0], C.ptr(samples), n_hyp, C.ptr(T), C.ptr(status), C.stream_ptr()),
+            "r3d_%s_hypotheses" % kind)
+    return T, status

@@ -175,6 +175,20 @@ int r3d_ransac3d_score(const double* T, int n_hyp, const double* P, const double
                        double thresh, int32_t* counts_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * K6  minimal-sample hypothesis generation, one hypothesis per thread
+ *   r3d_rigid_hypotheses:  3 correspondences -> rigid 4x4, utils/r3d.py:22-60 rigid_transform_3D on the sample
+ *   r3d_affine_hypotheses: 4 correspondences -> affine 4x4, utils/transformation3d.py:163-180
+ *                          homo_rigid_transform_3d on the sample (exactly determined: a 4x4 solve)
+ *   P, Q: xyzw doubles (n_pts); samples: int32 [n_hyp, 3 | 4] indices into P/Q, drawn by the caller (the
+ *   reference samples with NumPy's global RNG); T_out: [n_hyp, 16]; status_out (optional) int32 [n_hyp]:
+ *   0 ok, 1 degenerate sample (repeated / collinear / coplanar points: the fit is not unique).
+ * ------------------------------------------------------------------------------------ */
+int r3d_rigid_hypotheses(const double* P, const double* Q, int n_pts, const int32_t* samples, int n_hyp,
+                         double* T_out, int32_t* status_out, void* stream);
+int r3d_affine_hypotheses(const double* P, const double* Q, int n_pts, const int32_t* samples, int n_hyp,
+                          double* T_out, int32_t* status_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * K5  brute-force descriptor matching with cross-check (the step before RANSAC)
  *   replaces cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2) as called at
  *   utils/transformation3d.py:31-32 (OpenCV is a third-party dependency of the reference, not vendored).

@@ -155,3 +155,44 @@ def test_ransac3d_ragged_sizes():
         got = ops.ransac3d_score(torch.from_numpy(hyps).cuda(), ops.pack_xyzw(torch.from_numpy(P).cuda()),
                                  ops.pack_xyzw(torch.from_numpy(Q).cuda())).cpu().numpy()
         assert np.array_equal(got, want), (n, nh)
+
+
+@pytest.mark.parametrize("kind", ["rigid", "affine"])
+def test_device_hypotheses_match_the_reference_estimators(kind):
+    """K6: hypotheses generated on the device from minimal samples vs the oracle's per-sample calls of the
+    reference estimators (r3d.rigid_transform_3D / homo_rigid_transform_3d), and the full device-resident
+    sweep (generate + score) vs host-generated hypotheses scored by the oracle."""
+    import contextlib
+    import io
+    import torch
+    ops = sub("ops")
+    rng = np.random.default_rng(21)
+    n = 20000
+    P = rng.uniform(-1000, 1000, (n, 3)).astype(np.float32).astype(np.float64)
+    ang = 0.25
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    T[:3, 3] = [12, -7, 30]
+    Q = O.get_transformed_points(P, T) + rng.normal(size=(n, 3))
+    k = 3 if kind == "rigid" else 4
+    samples = np.random.RandomState(5).randint(n, size=(3000, k)).astype(np.int32)
+    samples[7, 1] = samples[7, 0]                      # a repeated index: degenerate
+    Pd = ops.pack_xyzw(torch.from_numpy(P).cuda())
+    Qd = ops.pack_xyzw(torch.from_numpy(Q).cuda())
+    Td, status = ops.hypotheses_3d(Pd, Qd, torch.from_numpy(samples).cuda(), kind)
+    Th, status = Td.cpu().numpy(), status.cpu().numpy()
+    assert status[7] == 1 and status.sum() < 30
+    ok = np.nonzero(status == 0)[0][:600]
+    with contextlib.redirect_stdout(io.StringIO()):
+        want = O.rigid_hypotheses(P, Q, samples[ok]) if kind == "rigid" else O.affine_hypotheses(P, Q, samples[ok])
+    if kind == "rigid":
+        np.testing.assert_allclose(Th[ok], want, rtol=0, atol=1e-7)
+        assert np.allclose(np.linalg.det(Th[ok][:, :3, :3]), 1.0, atol=1e-12)
+    else:
+        # exactly determined systems: GE vs LAPACK lstsq differ by conditioning x eps
+        scale = np.maximum(np.abs(want).max(axis=(1, 2), keepdims=True), 1.0)
+        assert np.median(np.abs(Th[ok] - want) / scale) < 1e-10
+        assert (np.abs(Th[ok] - want) / scale).max() < 1e-5
+    # device-resident sweep: counts of the device hypotheses = oracle counts of the same matrices
+    counts = ops.ransac3d_score(Td, Pd, Qd).cpu().numpy()
+    assert np.array_equal(counts[ok], O.score_hypotheses_3d(Th[ok], P, Q))
