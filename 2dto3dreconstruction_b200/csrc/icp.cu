@@ -556,6 +556,9 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     __shared__ GridParams g;
     __shared__ double T[12], D[12];
     __shared__ int s_n, s_done;
+    // the grid's base pointers live in shared memory: with 64 registers per thread the compiler would otherwise
+    // recompute these 64-bit addresses inside every loop of the search
+    __shared__ GridView s_view;
     __shared__ __align__(16) double scratch[NN_THREADS / 32][8 * 33];      // moment reduction scratch (two passes of 8)
     // survivors list of each warp; never shared with the reduction: its stale slots must stay real points
     __shared__ double2 lists[NN_THREADS / 32][LEAN_WARP_SMEM];
@@ -563,6 +566,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         g = w.grid.params[pair];
         s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
+        s_view = grid_view(w.grid, pair);
     }
     if (threadIdx.x < 12) {
         T[threadIdx.x] = w.state[pair].T[threadIdx.x];
@@ -571,7 +575,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     __syncthreads();
     if (s_done) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const GridView v = grid_view(w.grid, pair);
+    const GridView& v = s_view;
     const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
     int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
     float* budget = w.budget + (size_t)pair * w.max_src;
