@@ -10,6 +10,7 @@
 // The tile is walked in rounds of 256 consecutive pixels so that consecutive threads read
 // consecutive pixels and, after compaction, write consecutive points.
 #include "common.cuh"
+#include <type_traits>
 
 namespace r3d {
 
@@ -103,7 +104,19 @@ bp_scan(const int32_t* __restrict__ tile_count, int32_t* __restrict__ tile_base,
     if (threadIdx.x == 0) frame_offsets[frames] = carry;
 }
 
-template <typename T, int MODE, int LAYOUT>
+// n / b for the reference's intrinsics (utils/utils.py:63-66: fx = fy = 525, cx = 319.5, cy = 239.5) on frames of
+// at most 640 x 480 uint16 pixels: reciprocal multiply + one fused residual correction (Markstein) instead of the
+// ~35-instruction IEEE division routine.  The result equals the correctly rounded quotient for EVERY numerator the
+// domain can produce, (u - 319.5) * d and (v - 239.5) * d with d in 0..65535: checked exhaustively against NumPy by
+// tests/test_gpu_backproject.py::test_fast_division_is_exact_over_the_whole_uint16_domain.  Any other intrinsics,
+// size or depth type take __ddiv_rn.
+__device__ __forceinline__ double div_markstein(double n, double b, double rb) {
+    const double q = n * rb;
+    const double e = fma(-q, b, n);
+    return fma(e, rb, q);
+}
+
+template <typename T, int MODE, int LAYOUT, bool FASTDIV>
 __global__ void __launch_bounds__(BP_THREADS)
 bp_write(const T* __restrict__ depth, int hw, int width, int tiles_per_frame, double fx, double fy, double cx,
          double cy, double zscale, const int32_t* __restrict__ tile_base, const int32_t* __restrict__ frame_offsets,
@@ -161,8 +174,13 @@ bp_write(const T* __restrict__ depth, int hw, int width, int tiles_per_frame, do
         double x, y;
         if (MODE == R3D_BP_PINHOLE) {
             // ((u - cx) * d) / fx, in this order, IEEE double: bit-exact with utils/utils.py:72
-            x = __ddiv_rn(__dmul_rn((double)u - cx, dv), fx);
-            y = __ddiv_rn(__dmul_rn((double)v - cy, dv), fy);
+            if (FASTDIV) {
+                x = div_markstein(__dmul_rn((double)u - cx, dv), fx, 1.0 / 525.0);
+                y = div_markstein(__dmul_rn((double)v - cy, dv), fy, 1.0 / 525.0);
+            } else {
+                x = __ddiv_rn(__dmul_rn((double)u - cx, dv), fx);
+                y = __ddiv_rn(__dmul_rn((double)v - cy, dv), fy);
+            }
         } else {
             x = (double)u;
             y = (double)v;
@@ -191,10 +209,17 @@ static int bp_dispatch(const T* depth, int frames, int height, int width, int mo
     dim3 grid(tiles, frames);
     R3D_LAUNCH((bp_count<T>), grid, BP_THREADS, 0, st, depth, hw, tiles, zscale, tile_count);
     R3D_LAUNCH(bp_scan, 1, 1024, 0, st, tile_count, tile_base, frames * tiles, tiles, frames, out_offsets);
+    // the reference's hard-coded intrinsics on a uint16 frame no larger than 640 x 480: exact fast division
+    const bool fast = std::is_same<T, uint16_t>::value && mode == R3D_BP_PINHOLE && fx == 525.0 && fy == 525.0 && cx == 319.5 &&
+                      cy == 239.5 && width <= 640 && height <= 480;
 #define BP_CASE(M, L)                                                                                            \
     if (mode == M && layout == L) {                                                                              \
-        R3D_LAUNCH((bp_write<T, M, L>), grid, BP_THREADS, 0, st, depth, hw, width, tiles, fx, fy, cx, cy,        \
-                   zscale, tile_base, out_offsets, out);                                                         \
+        if (fast)                                                                                                \
+            R3D_LAUNCH((bp_write<T, M, L, true>), grid, BP_THREADS, 0, st, depth, hw, width, tiles, fx, fy, cx,  \
+                       cy, zscale, tile_base, out_offsets, out);                                                 \
+        else                                                                                                     \
+            R3D_LAUNCH((bp_write<T, M, L, false>), grid, BP_THREADS, 0, st, depth, hw, width, tiles, fx, fy, cx, \
+                       cy, zscale, tile_base, out_offsets, out);                                                 \
         return R3D_OK;                                                                                           \
     }
     BP_CASE(R3D_BP_PIXEL, R3D_POINTS_XYZ)

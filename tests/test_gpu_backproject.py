@@ -70,3 +70,26 @@ def test_ragged_sizes_and_layouts():
         got32 = p32[:int(off32[-1])].cpu().numpy()
         want32 = np.concatenate([O.depth_to_voxel_ld(img[f]) for f in range(2)]).astype(np.float32)
         assert np.array_equal(got32[:, :3], want32)
+
+
+def test_fast_division_is_exact_over_the_whole_uint16_domain():
+    """K1 divides by the reference's fx = fy = 525 with a reciprocal multiply and one fused correction instead of the
+    IEEE division routine.  That is bit-exact only if it returns the correctly rounded quotient for every numerator the
+    domain can produce: (u - 319.5) * d for u in 0..639 and (v - 239.5) * d for v in 0..479, d in 0..65535.  Enumerate
+    all of them against NumPy's division."""
+    import torch
+    ops = sub("ops")
+    u = np.arange(640, dtype=np.int64)[None, None, :]
+    v = np.arange(480, dtype=np.int64)[None, :, None]
+    plans = [(137, lambda f: (f * 480 + v) + 0 * u),          # every d for every column u
+             (103, lambda f: (f * 640 + u) + 0 * v)]          # every d for every row v
+    for n_frames, pattern in plans:
+        for first in range(0, n_frames, 16):
+            f = np.arange(first, min(n_frames, first + 16), dtype=np.int64)[:, None, None]
+            depth = (pattern(f) & 0xffff).astype(np.uint16)
+            pts, off = ops.backproject(torch.from_numpy(depth).cuda(), mode=ops.BP_PINHOLE, layout=ops.LAYOUT_XYZ)
+            got, off = pts.cpu().numpy(), off.cpu().numpy()
+            for k in range(depth.shape[0]):
+                want = O.depth_to_voxel_ld(depth[k])
+                assert off[k + 1] - off[k] == want.shape[0]
+                assert np.array_equal(got[off[k]:off[k + 1]], want), (first + k)
