@@ -205,3 +205,41 @@ def test_search_skipping_and_search_variants_do_not_change_results():
         d_mine = np.linalg.norm(src[diff] - B[idx[diff]], axis=1)
         assert np.all(np.abs(d_mine - db[diff]) <= 1e-9 * np.maximum(db[diff], 1.0)), "wrong neighbour after skipping"
     assert diff.size < 0.001 * len(A)
+
+
+def test_fuzz_against_the_oracle_icp():
+    """Random small registration problems (continuous coordinates, so no exact distance ties): surfaces and blobs,
+    every combination of partial_set_size / tolerance / iteration cap, with and without an initial pose.  The whole
+    trajectory must be the oracle's: same iteration count, transform equal to rounding."""
+    icp = sub("utils.icp")
+    rng = np.random.default_rng(77)
+    for case in range(30):
+        n = int(rng.integers(150, 2500))
+        m = int(rng.integers(150, 2500))
+        scale = 10.0 ** rng.uniform(-1, 3)
+        if rng.random() < 0.6:
+            xy = rng.uniform(-1, 1, size=(m, 2))
+            B = np.column_stack((xy, 0.4 * np.sin(2.5 * xy[:, 0]) * np.cos(1.5 * xy[:, 1])))
+            xy = rng.uniform(-0.9, 0.9, size=(n, 2))
+            A = np.column_stack((xy, 0.4 * np.sin(2.5 * xy[:, 0]) * np.cos(1.5 * xy[:, 1])))
+        else:
+            B = rng.normal(size=(m, 3))
+            A = B[rng.integers(0, m, n)] + rng.normal(size=(n, 3)) * 0.02
+        ang = rng.uniform(-0.15, 0.15, size=3)
+        cx, cy, cz = np.cos(ang)
+        sx, sy, sz = np.sin(ang)
+        R = (np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+             @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]))
+        A = (A @ R.T + rng.normal(size=3) * 0.1 + rng.normal(size=(n, 3)) * 0.003) * scale
+        B = B * scale
+        kw = dict(max_iterations=int(rng.choice([1, 5, 20, 40])), tolerance=float(rng.choice([0.0, 1e-3 * scale, 1e-6 * scale])),
+                  partial_set_size=float(rng.choice([1.0, 0.8, 0.5])))
+        if rng.random() < 0.3:
+            init = np.eye(4)
+            init[:3, 3] = rng.normal(size=3) * 0.05 * scale
+            kw["init_pose"] = init
+        T, dist, it = icp.icp(A, B, **kw)
+        Tr, dr, itr = O.icp(A, B, **kw)
+        assert it == itr, (case, kw)
+        assert_transform_parity(T, Tr, O.scene_extent(B), "case %d %r" % (case, kw), rot_tol=1e-8, trans_tol=1e-9)
+        np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=0, atol=1e-8 * O.scene_extent(B))

@@ -102,3 +102,47 @@ def test_batched_pairs_ragged():
         db, ib = O.nearest_neighbor_brute(srcs[p], dsts[p])
         assert np.array_equal(idx[so[p]:so[p + 1]], ib), p
         np.testing.assert_allclose(dist[so[p]:so[p + 1]], db, rtol=1e-14)
+
+
+def test_fuzz_against_brute_force():
+    """Many small random configurations -- scales from 1e-3 to 1e6, anisotropic and degenerate extents, clusters,
+    queries inside, outside and far from the destination cloud, tiny and lopsided sizes -- every answer must be
+    brute force's, bit for bit (index and squared distance)."""
+    icp = sub("utils.icp")
+    rng = np.random.default_rng(2024)
+    for case in range(120):
+        n = int(rng.choice([1, 2, 3, 31, 32, 33, 100, 500, 1500, 3000]))
+        m = int(rng.choice([1, 2, 5, 64, 300, 1000, 2500]))
+        scale = 10.0 ** rng.uniform(-3, 6)
+        aniso = 10.0 ** rng.uniform(-3, 0, size=3) if rng.random() < 0.4 else np.ones(3)
+        kind = rng.integers(0, 5)
+        if kind == 0:        # gaussian blob
+            dst = rng.normal(size=(m, 3))
+        elif kind == 1:      # surface z = f(x, y)
+            xy = rng.uniform(-1, 1, size=(m, 2))
+            dst = np.column_stack((xy, 0.3 * np.sin(3 * xy[:, 0]) + 0.2 * xy[:, 1] ** 2))
+        elif kind == 2:      # a few tight clusters far apart
+            centres = rng.normal(size=(4, 3)) * 5
+            dst = centres[rng.integers(0, 4, m)] + rng.normal(size=(m, 3)) * 0.01
+        elif kind == 3:      # lattice: exact ties
+            dst = rng.integers(0, 5, size=(m, 3)).astype(float)
+        else:                # uniform cube
+            dst = rng.uniform(-1, 1, size=(m, 3))
+        where = rng.integers(0, 4)
+        if where == 0:       # queries drawn like the destination, slightly moved
+            src = dst[rng.integers(0, m, n)] + rng.normal(size=(n, 3)) * 0.02
+        elif where == 1:     # same region
+            src = rng.uniform(-1.2, 1.2, size=(n, 3))
+        elif where == 2:     # shifted well outside
+            src = rng.normal(size=(n, 3)) + rng.choice([-1, 1], size=3) * 20
+        else:                # a mixture with a few enormous outliers
+            src = rng.uniform(-1, 1, size=(n, 3))
+            src[rng.random(n) < 0.05] *= 1e4
+        if kind == 3:
+            src = np.round(src * 2) / 2
+        dst = dst * aniso * scale
+        src = src * aniso * scale
+        d, i = icp.nearest_neighbor(src, dst)
+        db, ib = O.nearest_neighbor_brute(src, dst)
+        assert np.array_equal(i, ib), (case, n, m, kind, where, scale)
+        np.testing.assert_allclose(d, db, rtol=1e-14, atol=0, err_msg=str(case))
