@@ -329,10 +329,17 @@ def main():
                         "note": "kernel timed alone; nominal peak: 16 fp64 lanes/clk/SMSP x 592 SMSPs x 1965 MHz; evaluations "
                                 "per correspondence searched from the counter build (profiles/r01_nn_sweeps.md); skipped "
                                 "searches make the effective figure lower in late iterations"}
+    # DRAM traffic of the kernel from the committed ncu capture, scaled from the capture's launch size (8 pairs) to
+    # this run's (pairs_per_chunk pairs): bytes per correspondence x correspondences per launch
     traffic_file = os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
+            tf = json.load(open(traffic_file))
+            per_corr = tf["dram_bytes_per_launch"] / float(tf["correspondences_per_launch"])
+            corr_per_launch = corr_per_step * args.steps / max(int(nn_launches.value), 1)
+            roofline["traffic"] = per_corr * corr_per_launch
+            roofline["traffic_bytes_per_correspondence"] = per_corr
+            roofline["traffic_source"] = tf.get("source")
         except Exception:
             pass
 
