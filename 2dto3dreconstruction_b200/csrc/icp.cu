@@ -704,9 +704,14 @@ sel_hist_kernel(IcpWorkspace w, int pass) {
             in = (pass == 0) || ((key >> (shift + sel_bits(pass))) == sel.prefix);
             d = (uint32_t)(key >> shift) & mask;
         }
-        // lanes outside the prefix form singleton groups that never touch the bins
-        const unsigned grp = __match_any_sync(0xffffffffu, in ? d : (SEL_BINS + (uint32_t)lane));
-        if (in && (grp & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(grp));
+        // after the first passes almost no key still matches the prefix: warps without a match only stream
+        const unsigned active = __ballot_sync(0xffffffffu, in);
+        if (active == 0u) continue;
+        if (in) {
+            // warp-aggregated increment among the lanes that match (early passes put every key in a few bins)
+            const unsigned grp = __match_any_sync(active, d);
+            if ((grp & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(grp));
+        }
     }
     __syncthreads();
     uint32_t* gh = w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS;
