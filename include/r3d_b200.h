@@ -227,12 +227,14 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
                                   int32_t* n_src_out_host, int32_t* n_dst_out_host,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
-/* Tuning knobs; none of them changes results.  R3D_OPT_GROUP_SIZE: lanes that share one staged
- * candidate list in the NN search (8, 16 or 32).  R3D_OPT_CELL_FACTOR: automatic grid cell edge in
- * units of the estimated point spacing (used when cell_size <= 0).  R3D_OPT_NN_IMPL: 1 = lean
- * group-union walk (default), 0 = staged candidate lists.  R3D_OPT_SLACK_MULT / R3D_OPT_SLACK_MAX_FRAC: how
- * much larger than its bound a seeded search ball is made (multiple of the query's movement in this
- * iteration, capped at a fraction of the cell edge; 0 disables search skipping). */
+/* Tuning knobs; none of them changes results (process-wide, read when a call is issued).
+ *   R3D_OPT_NN_IMPL        1 = warp-union walk (default, csrc/lean_search.cuh), 0 = staged group lists (csrc/coop_search.cuh)
+ *   R3D_OPT_GROUP_SIZE     staged implementation only: lanes that share one candidate list (8, 16 or 32)
+ *   R3D_OPT_CELL_FACTOR    automatic grid cell edge in units of the estimated point spacing (used when cell_size <= 0; default 2)
+ *   R3D_OPT_SLACK_MULT, R3D_OPT_SLACK_MAX_FRAC
+ *                          how much larger than its bound a seeded search ball is made: a multiple of the query's movement in
+ *                          this iteration (default 8), used while that is at most a fraction of the cell edge (default 0.25);
+ *                          a multiple of 0 disables the skipping of searches that cannot change the neighbour */
 typedef enum {
     R3D_OPT_GROUP_SIZE = 1, R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5
 } r3d_option;
