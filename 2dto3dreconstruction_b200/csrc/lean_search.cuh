@@ -272,7 +272,10 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
 // finished once its best distance is within the radius it asked for (nothing unseen can be closer),
 // otherwise its rcap doubles.  Lanes left out wait for a later round with a leader near them.  Lanes
 // that arrive with a seed ask for their full ball at once, so a coherent warp takes one round.
-constexpr int LEAN_WIN = 4;      // served: box inside the leader's box widened by max(4 cells, its own extent)
+#ifndef R3D_LEAN_WIN
+#define R3D_LEAN_WIN 4
+#endif
+constexpr int LEAN_WIN = R3D_LEAN_WIN;      // served: box inside the leader's box widened by max(4 cells, its own extent)
 
 // float -> int map that preserves order under SIGNED comparison (and is its own inverse)
 __device__ __forceinline__ int f2sord(float f) {
