@@ -618,8 +618,10 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
                     const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
                     const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
-                    // rounded up, with room for the rounding of the two transformed positions themselves
-                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f + 1e-30f;
+                    // rounded up; the last term covers the fp64 rounding of the two transformed positions themselves
+                    // (a few ulps of the coordinates), which matters only when coordinates are ~1e9 times the distances
+                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
+                                        __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
                     left = __fsub_rd(budget[i], __fmul_ru(2.0f, moved));
                     skip = left > 0.0f;
                     const float want = moved * tune.slack_mult;

@@ -243,3 +243,32 @@ def test_fuzz_against_the_oracle_icp():
         assert it == itr, (case, kw)
         assert_transform_parity(T, Tr, O.scene_extent(B), "case %d %r" % (case, kw), rot_tol=1e-8, trans_tol=1e-9)
         np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=0, atol=1e-8 * O.scene_extent(B))
+
+
+@pytest.mark.parametrize("offset", [0.0, 1.0e5, 3.0e7])
+def test_search_skipping_is_exact_far_from_the_origin(offset):
+    """The skip budgets rest on rounded fp64 positions; with coordinates up to 1e7 times the neighbour distances the
+    result with skipping must still equal, bit for bit, the result with skipping disabled."""
+    ops = sub("ops")
+    C = sub("_capi")
+    L = C.lib()
+    rng = np.random.default_rng(int(offset) % 97 + 3)
+    xy = rng.uniform(-40, 40, size=(6000, 2))
+    B = np.column_stack((xy, 6 * np.sin(xy[:, 0] / 9) * np.cos(xy[:, 1] / 7)))
+    ang = 0.03
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    A = B[rng.permutation(6000)[:5000]] @ R.T + np.array([0.8, -0.5, 0.3]) + rng.normal(size=(5000, 3)) * 0.05
+    A = A + offset
+    B = B + offset
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    so, do = ops._offsets([len(A)]), ops._offsets([len(B)])
+    try:
+        on = ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=40, tolerance=0.0, want_last=True)
+        assert L.r3d_set_option(4, 0.0) == 0
+        off = ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=40, tolerance=0.0, want_last=True)
+    finally:
+        L.r3d_set_option(4, 8.0)
+    assert np.array_equal(on["T"].cpu().numpy(), off["T"].cpu().numpy())
+    assert np.array_equal(on["idx"].cpu().numpy(), off["idx"].cpu().numpy())
+    assert np.array_equal(on["dist"].cpu().numpy(), off["dist"].cpu().numpy())
