@@ -93,10 +93,20 @@ __device__ __forceinline__ void consider(Best& b, const Point4* __restrict__ pts
 // [lo, hi], pruning (y,z) rows whose distance lower bound already exceeds the best.
 __device__ __forceinline__ void scan_block_box(Best& best, const GridView& v, const GridParams& g, int b, int cbx, int cby,
                                                int cbz, int lox, int loy, int loz, int hix, int hiy, int hiz, double qx,
-                                               double qy, double qz, double tqy, double tqz) {
+                                               double qy, double qz, double tqx, double tqy, double tqz) {
     const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
     const int y0 = max(loy, cby * 4), y1 = min(hiy, cby * 4 + 3);
     const int z0 = max(loz, cbz * 4), z1 = min(hiz, cbz * 4 + 3);
+    // gap in cell units between the query and the x-range of cells that will be read; with the (y,z) gaps below it
+    // prunes whole rows -- and for a query far outside the cloud, whose box covers everything, nearly all of them
+    double gx = fmax(fmax((double)(cbx * 4 + x0) - tqx, tqx - (double)(cbx * 4 + x1 + 1)), 0.0);
+    gx = fmax(gx - 1e-6, 0.0) * g.cell;
+    {   // the block as a whole
+        double by_ = fmax(fmax((double)y0 - tqy, tqy - (double)(y1 + 1)), 0.0), bz_ = fmax(fmax((double)z0 - tqz, tqz - (double)(z1 + 1)), 0.0);
+        by_ = fmax(by_ - 1e-6, 0.0) * g.cell;
+        bz_ = fmax(bz_ - 1e-6, 0.0) * g.cell;
+        if (gx * gx + by_ * by_ + bz_ * bz_ > best.d2) return;
+    }
     const uint32_t* cs = v.cell_start + (size_t)b * 64;
     for (int iz = z0; iz <= z1; iz++) {
         // gap in cell units between the query and the slab [iz, iz+1); 1e-6 cells of slack
@@ -106,7 +116,7 @@ __device__ __forceinline__ void scan_block_box(Best& best, const GridView& v, co
         for (int iy = y0; iy <= y1; iy++) {
             double gy = fmax(fmax((double)iy - tqy, tqy - (double)(iy + 1)), 0.0);
             gy = fmax(gy - 1e-6, 0.0) * g.cell;
-            if (gz * gz + gy * gy > best.d2) continue;
+            if (gx * gx + gz * gz + gy * gy > best.d2) continue;
             const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
             const uint32_t s = __ldg(cs + f + x0);
             const uint32_t e = __ldg(cs + f + x1 + 1);
@@ -138,7 +148,7 @@ __device__ __forceinline__ void bounded_search(Best& best, const GridView& v, co
                 for (int cbx = bx0; cbx <= bx1; cbx++) {
                     const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
                     const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
-                    if (b >= 0) scan_block_box(best, v, g, b, cbx, cby, cbz, lox, loy, loz, hix, hiy, hiz, qx, qy, qz, tqy, tqz);
+                    if (b >= 0) scan_block_box(best, v, g, b, cbx, cby, cbz, lox, loy, loz, hix, hiy, hiz, qx, qy, qz, tqx, tqy, tqz);
                 }
     } else {
         // far query: the box covers more block slots than there are blocks; walk the block list
@@ -148,7 +158,7 @@ __device__ __forceinline__ void bounded_search(Best& best, const GridView& v, co
             const int cby = (int)((key / (uint32_t)g.bx) % (uint32_t)g.by);
             const int cbz = (int)(key / ((uint32_t)g.bx * (uint32_t)g.by));
             if (cbx < bx0 || cbx > bx1 || cby < by0 || cby > by1 || cbz < bz0 || cbz > bz1) continue;
-            scan_block_box(best, v, g, b, cbx, cby, cbz, lox, loy, loz, hix, hiy, hiz, qx, qy, qz, tqy, tqz);
+            scan_block_box(best, v, g, b, cbx, cby, cbz, lox, loy, loz, hix, hiy, hiz, qx, qy, qz, tqx, tqy, tqz);
         }
     }
 }

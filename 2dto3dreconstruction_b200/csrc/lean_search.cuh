@@ -21,8 +21,10 @@
 //      lexicographic minimum of (squared distance, cloud index) in fp64.
 // A lane may evaluate points it did not need (they are real points of the cloud, so any of them
 // is a valid bound), which is why nothing in the scan is predicated per lane.
-// Boxes with more than LEAN_SEG_CAP segments (far outliers, queries far outside the cloud) fall
-// back to the per-lane bounded search of grid.cuh, which has the block-list mode.
+// Boxes with many row segments are walked block by block (one segment = one block's points); boxes of
+// more than LEAN_BLOCKS_MAX blocks (far outliers, queries far outside the cloud, badly misaligned pairs) are
+// handled one query at a time by the whole warp: blocks are pruned by their distance to the query and the
+// survivors scanned 32 points at a time (far_query_search).
 #pragma once
 #include "coop_search.cuh"
 
@@ -38,7 +40,14 @@
 
 namespace r3d {
 
-constexpr int LEAN_SEG_CAP = 2048;     // segments per round the warp walk accepts
+#ifndef R3D_LEAN_ROW_SEGS_MAX
+#define R3D_LEAN_ROW_SEGS_MAX 96
+#endif
+#ifndef R3D_LEAN_BLOCKS_MAX
+#define R3D_LEAN_BLOCKS_MAX 256
+#endif
+constexpr int LEAN_ROW_SEGS_MAX = R3D_LEAN_ROW_SEGS_MAX;  // boxes with more row segments than this are walked block by block
+constexpr int LEAN_BLOCKS_MAX = R3D_LEAN_BLOCKS_MAX;      // ... and boxes with more blocks than this go to the per-lane search
 constexpr int LEAN_LIST_CAP = 64;      // survivors list: at most LEAN_FLUSH - 1 + 32 entries between flushes
 #ifndef R3D_LEAN_FLUSH
 #define R3D_LEAN_FLUSH 24
@@ -132,7 +141,7 @@ __device__ __forceinline__ void list_init(double2* list, const Point4* __restric
     __syncwarp();
 }
 
-// Walk every cell of the warp's box [lo, hi] (warp-uniform ints, at most LEAN_SEG_CAP segments).
+// Walk every cell of the warp's box [lo, hi] (warp-uniform ints; size limits: see lean_search).
 __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_pos, const GridView& v, const GridParams& g, int lox,
                                               int loy, int loz, int hix, int hiy, int hiz, double qx, double qy, double qz) {
     const int lane = threadIdx.x & 31;
@@ -141,28 +150,44 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
     const int bx0 = lox >> 2, bx1 = hix >> 2;
     const int nxb = bx1 - bx0 + 1;
     const int nseg = ny * nz * nxb;
-    // exact for the small integers involved (nseg <= LEAN_SEG_CAP): quotient by reciprocal, then fix up
-    const float inv_nxb = 1.0f / (float)nxb, inv_ny = 1.0f / (float)ny;
-    R3D_STAT(5, nseg);
-    for (int base = 0; base < nseg; base += 32) {
+    // Large boxes (misaligned clouds, outliers: the ball is many cells wide) are mostly empty rows.  They are walked
+    // block by block instead: one segment = all points of a block (contiguous in the sorted cloud), an order of
+    // magnitude fewer lookups, and the filter box drops the extra points when they are loaded.
+    const int by0 = loy >> 2, nby = (hiy >> 2) - by0 + 1, bz0 = loz >> 2, nbz = (hiz >> 2) - bz0 + 1;
+    const int nblk = nxb * nby * nbz;
+    const bool by_block = nseg > LEAN_ROW_SEGS_MAX;      // warp-uniform
+    const int n_units = by_block ? nblk : nseg;
+    // exact for the small integers involved (a few hundred units): quotient by reciprocal, then fix up
+    const int d0 = nxb, d1 = by_block ? nby : ny;
+    const float inv_d0 = 1.0f / (float)d0, inv_d1 = 1.0f / (float)d1;
+    R3D_STAT(5, n_units);
+    for (int base = 0; base < n_units; base += 32) {
         R3D_STAT(4, 1);
         const int sidx = base + lane;
         uint32_t s = 0, cnt = 0;
-        if (sidx < nseg) {
-            int row = (int)((float)sidx * inv_nxb);
-            row += (sidx - row * nxb >= nxb) - (sidx - row * nxb < 0);
-            const int j = sidx - row * nxb;
-            int rz = (int)((float)row * inv_ny);
-            rz += (row - rz * ny >= ny) - (row - rz * ny < 0);
-            const int iy = loy + (row - rz * ny), iz = loz + rz;
-            const int cbx = bx0 + j, cby = iy >> 2, cbz = iz >> 2;
+        if (sidx < n_units) {
+            // sidx = (k2 * d1 + k1) * d0 + k0
+            int row = (int)((float)sidx * inv_d0);
+            row += (sidx - row * d0 >= d0) - (sidx - row * d0 < 0);
+            const int k0 = sidx - row * d0;
+            int k2 = (int)((float)row * inv_d1);
+            k2 += (row - k2 * d1 >= d1) - (row - k2 * d1 < 0);
+            const int k1 = row - k2 * d1;
+            const int cbx = bx0 + k0;
+            const int cby = by_block ? by0 + k1 : (loy + k1) >> 2, cbz = by_block ? bz0 + k2 : (loz + k2) >> 2;
             const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
             const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
             if (b >= 0) {
-                const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
-                const uint32_t* cs = v.cell_start + (size_t)b * 64 + (((iz & 3) << 4) | ((iy & 3) << 2));
-                s = __ldg(cs + x0);
-                cnt = __ldg(cs + x1 + 1) - s;
+                if (by_block) {
+                    s = __ldg(v.block_first + b);
+                    cnt = __ldg(v.block_first + b + 1) - s;
+                } else {
+                    const int iy = loy + k1, iz = loz + k2;
+                    const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
+                    const uint32_t* cs = v.cell_start + (size_t)b * 64 + (((iz & 3) << 4) | ((iy & 3) << 2));
+                    s = __ldg(cs + x0);
+                    cnt = __ldg(cs + x1 + 1) - s;
+                }
             }
         }
         // candidate stream = concatenation of the 32 segments; stream index t lives in the segment j
@@ -277,6 +302,67 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
 #endif
 constexpr int LEAN_WIN = R3D_LEAN_WIN;      // served: box inside the leader's box widened by max(4 cells, its own extent)
 
+// All 32 lanes work for ONE query (lane `owner`'s): exact search of the ball of radius R around it when its box is far
+// too large for the union walk (a far outlier, a query far outside the cloud, a badly misaligned pair).  The block
+// list is swept 32 blocks at a time: a lane computes the distance from the query to its block's bounding box and the
+// blocks that can reach into the ball are scanned by the whole warp, 32 points at a time.  Every point within R of
+// the query is evaluated (the seed excepted), so afterwards nothing unseen is closer than R.  Returns, on every lane,
+// the lexicographic minimum of (squared distance, cloud index) over the evaluated points other than the seed, and
+// whether every block was scanned.
+__device__ __forceinline__ Best far_query_search(int owner, const Best& seed, const GridView& v, const GridParams& g, double qx,
+                                                 double qy, double qz, float R, bool& all_scanned) {
+    const int lane = threadIdx.x & 31;
+    const double ax = __shfl_sync(0xffffffffu, qx, owner), ay = __shfl_sync(0xffffffffu, qy, owner), az = __shfl_sync(0xffffffffu, qz, owner);
+    const int seed_pos = __shfl_sync(0xffffffffu, seed.pos, owner);
+    const float Rw = __shfl_sync(0xffffffffu, R, owner);
+    // squared reach, rounded up generously (the block test only has to be conservative)
+    const double reach2 = (Rw < 1e18f) ? (double)Rw * (double)Rw * (1.0 + 1e-5) : CUDART_INF;
+    const double bw = 4.0 * g.cell, pad = 1e-6 * g.cell;
+    Best loc;
+    loc.d2 = CUDART_INF; loc.idx = 0x7fffffff; loc.pos = -1;
+    bool all = true;
+    for (int b0 = 0; b0 < g.n_blocks; b0 += 32) {
+        const int b = b0 + lane;
+        bool hit = false;
+        if (b < g.n_blocks) {
+            const uint32_t key = __ldg(v.block_key + b);
+            const int cbx = (int)(key % (uint32_t)g.bx);
+            const int cby = (int)((key / (uint32_t)g.bx) % (uint32_t)g.by);
+            const int cbz = (int)(key / ((uint32_t)g.bx * (uint32_t)g.by));
+            const double lx = g.ox + (double)cbx * bw - pad, ly = g.oy + (double)cby * bw - pad, lz = g.oz + (double)cbz * bw - pad;
+            const double dx = fmax(fmax(lx - ax, ax - (lx + bw + 2.0 * pad)), 0.0);
+            const double dy = fmax(fmax(ly - ay, ay - (ly + bw + 2.0 * pad)), 0.0);
+            const double dz = fmax(fmax(lz - az, az - (lz + bw + 2.0 * pad)), 0.0);
+            hit = !(dx * dx + dy * dy + dz * dz > reach2);      // (the grid spans the cloud's bounding box: no point lies outside its block)
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int in_range = min(32, g.n_blocks - b0);
+        all = all && (__popc(m) == in_range);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1u;
+            const uint32_t s0 = __ldg(v.block_first + b0 + j), e0 = __ldg(v.block_first + b0 + j + 1);
+            for (uint32_t k = s0 + (uint32_t)lane; k < e0; k += 32) {
+                const double2* p = reinterpret_cast<const double2*>(v.pts + k);
+                const double2 xy = __ldg(p), zw = __ldg(p + 1);
+                const double ex = ax - xy.x, ey = ay - xy.y, ez = az - zw.x;
+                const double d2 = ex * ex + ey * ey + ez * ez;
+                const int idx = __double2loint(zw.y);
+                if ((int)k != seed_pos && (d2 < loc.d2 || (d2 == loc.d2 && idx < loc.idx))) { loc.d2 = d2; loc.idx = idx; loc.pos = (int)k; }
+            }
+        }
+    }
+    // lexicographic minimum over the lanes
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od2 = __shfl_xor_sync(0xffffffffu, loc.d2, o);
+        const int oidx = __shfl_xor_sync(0xffffffffu, loc.idx, o), opos = __shfl_xor_sync(0xffffffffu, loc.pos, o);
+        if (od2 < loc.d2 || (od2 == loc.d2 && oidx < loc.idx)) { loc.d2 = od2; loc.idx = oidx; loc.pos = opos; }
+    }
+    all_scanned = all;
+    return loc;
+}
+
 // float -> int map that preserves order under SIGNED comparison (and is its own inverse)
 __device__ __forceinline__ int f2sord(float f) {
     const int b = __float_as_int(f);
@@ -350,7 +436,10 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
         const int loz = __reduce_min_sync(FULL, part ? mloz : big), hiz = __reduce_max_sync(FULL, part ? mhiz : -1);
         const bool whole = lox == 0 && loy == 0 && loz == 0 && hix == g.nx - 1 && hiy == g.ny - 1 && hiz == g.nz - 1;
         const long long nseg = (long long)(hiy - loy + 1) * (hiz - loz + 1) * ((hix >> 2) - (lox >> 2) + 1);
-        if (nseg <= (long long)LEAN_SEG_CAP) {
+        const long long nblk = (long long)((hiy >> 2) - (loy >> 2) + 1) * ((hiz >> 2) - (loz >> 2) + 1) * ((hix >> 2) - (lox >> 2) + 1);
+        // small boxes are walked row by row, larger ones block by block; boxes of more than LEAN_BLOCKS_MAX blocks are
+        // searched one query at a time with distance pruning
+        if (nseg <= (long long)LEAN_ROW_SEGS_MAX || nblk <= (long long)LEAN_BLOCKS_MAX) {
             // the union of the served balls' bounding boxes in world coordinates: a point outside it is
             // outside every served ball.  When the box is the whole grid everything is looked at once and
             // the answer is final for every lane, so nothing may be filtered.
@@ -369,15 +458,22 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
                 rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the union) must not set the next radius
             }
         } else {
-            if (part) {
-                // far outliers / queries far outside the cloud: per-lane exact search with the block-list mode
-                Best b = (other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx)) ? other : seed;
-                if (!(b.d2 < CUDART_INF)) seed_search(b, v, g, qx, qy, qz);
-                bounded_search(b, v, g, qx, qy, qz);
-                if (b.pos != seed.pos) other = b;      // the exact neighbour; nothing is known about the runner-up
-                fin = true;
+            // far outliers / queries far outside the cloud / badly misaligned pairs: the served lanes are searched one
+            // at a time, the whole warp working for each (far_query_search)
+            unsigned todo = __ballot_sync(FULL, part);
+            while (todo) {
+                const int owner = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                bool all_scanned = false;
+                const Best found = far_query_search(owner, seed, v, g, qx, qy, qz, ruse, all_scanned);
+                if ((int)(threadIdx.x & 31) == owner) {
+                    if (found.d2 < other.d2 || (found.d2 == other.d2 && found.idx < other.idx)) other = found;
+                    const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
+                    fin = all_scanned || (rn <= ruse) || !(ruse < 1e37f);
+                    if (fin) cover = all_scanned ? inf : ruse;
+                    rcap *= 2.0f;
+                }
             }
-            __syncwarp();
         }
     }
 }
