@@ -65,7 +65,7 @@ struct IcpWorkspace {
     int nn_ctas;           // CTAs per pair of the persistent nn kernel
     int* vw_counter;       // [pair] next virtual warp of the running nn launch (reset by its consumer)
     int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
-    float* budget;         // [pair][max_src]  how far a query may still move before its neighbour can change (lean kernel)
+    float* budget;         // [pair][max_src]  lower bound of the distance from the query to every point but its neighbour (lean kernel)
     double* d2;            // [pair][max_src]
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
@@ -533,12 +533,13 @@ nn_kernel(IcpWorkspace w, int write_d2) {
 //
 // Skipping searches that cannot change the answer.  When a seeded search ends with the seed p still the
 // nearest point, it also knows a lower bound L2 of the distance to every OTHER point (the runner-up among
-// the evaluated points, or the radius it covered, whichever is smaller).  budget = L2 - d(q, p) is then
-// how much slack the answer has: if the query later moves by delta in total, p's distance grows by at
-// most delta and every other distance shrinks by at most delta (triangle inequality), so while
-// budget - 2 * sum(delta) > 0 the neighbour is still p, strictly, and no search is needed -- only the
-// exact new distance to p.  The per-iteration movement |T_k a - T_{k-1} a| is computed exactly per query
-// and subtracted from the stored budget with outward rounding.  To have a budget worth keeping, a seeded
+// the evaluated points, or the radius it covered, whichever is smaller); that bound is the query's stored
+// `budget`.  If the query later moves by delta in total, every other distance shrinks by at most delta
+// (triangle inequality), so while d(q_now, p) < L2 - sum(delta) the neighbour is still p, strictly, and no
+// search is needed -- only the exact new distance to p, which the seed evaluation computes anyway (a query
+// that moves TOWARDS its neighbour, the usual case in a converging ICP, keeps its budget longer than the
+// symmetric bound L2 - d - 2 sum(delta) > 0 would allow).  The per-iteration movement |T_k a - T_{k-1} a| is
+// computed exactly per query and subtracted from the stored bound with outward rounding.  To have a bound worth keeping, a seeded
 // lane asks for a ball a little larger than its bound (`slack`, proportional to its current movement):
 // costs a few candidates now, saves whole searches once ICP has nearly converged.
 struct LeanTuning {
@@ -606,7 +607,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             Best seed, other;
             seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
             other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
-            float left = 0.0f, slack = 0.0f;      // budget left after this iteration's movement
+            float left = 0.0f, slack = 0.0f;      // bound on the other points left after this iteration's movement
             bool skip = false;
             if (active) {
                 const Point4 a = load_point(src + i);
@@ -622,8 +623,8 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     // (a few ulps of the coordinates), which matters only when coordinates are ~1e9 times the distances
                     const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
                                         __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
-                    left = __fsub_rd(budget[i], __fmul_ru(2.0f, moved));
-                    skip = left > 0.0f;
+                    left = __fsub_rd(budget[i], moved);
+                    skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
                     const float want = moved * tune.slack_mult;
                     slack = (want <= slack_max) ? want + 1e-4f * slack_max : 0.0f;
                 }
@@ -647,8 +648,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 } else if (SEEDED && seed_wins) {
                     // lower bound of the distance to any point other than the seed, minus the seed's distance
                     // (float square roots: the 1e-6 factors cover their rounding)
-                    const float l2 = fminf(sqrtf(__double2float_rd(other.d2)), cover) * 0.999999f;
-                    nb = fmaxf(__fsub_rd(l2, sqrtf(__double2float_ru(seed.d2)) * 1.000001f), 0.0f);
+                    nb = fminf(sqrtf(__double2float_rd(other.d2)), cover) * 0.999999f;
                 }
                 budget[i] = nb;
             }
