@@ -59,6 +59,10 @@ SIGNATURES = {
     "r3d_match_workspace_bytes": (c_size_t, [c_int, c_int]),
     "r3d_match_descriptors": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                       c_void_p]),
+    "r3d_match_descriptors_ratio": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_double, c_void_p, c_void_p, c_void_p,
+                                            c_size_t, c_void_p]),
+    "r3d_voxel_downsample_workspace_bytes": (c_size_t, [c_int64]),
+    "r3d_voxel_downsample": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_register_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "r3d_register_depth_pairs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_double, c_double, c_double, c_double,
                                          ctypes.POINTER(IcpParams), c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -8,6 +8,12 @@
 // exact in float32 whatever the summation order: indices AND distances are bit-identical to OpenCV's.  For
 // general float descriptors the indices agree wherever the minima are not within rounding of each other.
 //
+// r3d_match_descriptors_ratio adds the second-best ratio test of skimage.feature.match_descriptors(des1, des2,
+// max_ratio=0.8, cross_check=True) as the reference calls it at utils/homography_utils/q8.py:90 (scikit-image 0.17.2,
+// requirements.txt:94, not vendored): after the mutual check a query is kept iff best / second_best < max_ratio,
+// where second_best is the smallest distance from the query to any OTHER train descriptor (0 replaced by DBL_EPSILON),
+// the distances being float64 square roots -- of exact integers for SIFT, so the test is bit-identical too.
+//
 // Sizes are small (hundreds to a few thousand descriptors of 128 floats, < 1 GFLOP): two launches of a
 // shared-memory tiled argmin kernel (queries->trains and trains->queries) and one cross-check pass.  No tensor
 // cores: the whole problem is a few microseconds of CUDA-core work and has to be exact.
@@ -25,7 +31,7 @@ constexpr int MT_Y_TILE = 32;                                    // Y rows stage
 __global__ void __launch_bounds__(MT_THREADS)
 bf_argmin_kernel(const float* __restrict__ A, int na, const float* __restrict__ B, int nb, int dim, int dim_pad,
                  int32_t* __restrict__ idx_ab, float* __restrict__ d2_ab, int32_t* __restrict__ idx_ba,
-                 float* __restrict__ d2_ba) {
+                 float* __restrict__ d2_ba, float* __restrict__ second_ab) {
     extern __shared__ float sm[];
     const bool rev = blockIdx.y == 1;
     const float* X = rev ? B : A;
@@ -42,10 +48,10 @@ bf_argmin_kernel(const float* __restrict__ A, int na, const float* __restrict__ 
         const int r = e / dim_pad, c = e - r * dim_pad;
         sX[e] = (x0 + r < nx && c < dim) ? X[(size_t)(x0 + r) * dim + c] : 0.0f;
     }
-    float best[MT_ROWS_PER_WARP];
+    float best[MT_ROWS_PER_WARP], second[MT_ROWS_PER_WARP];      // second: smallest distance to a row other than bidx
     int bidx[MT_ROWS_PER_WARP];
 #pragma unroll
-    for (int k = 0; k < MT_ROWS_PER_WARP; k++) { best[k] = __int_as_float(0x7f800000); bidx[k] = -1; }
+    for (int k = 0; k < MT_ROWS_PER_WARP; k++) { best[k] = second[k] = __int_as_float(0x7f800000); bidx[k] = -1; }
     const float* myX = sX + (size_t)warp * MT_ROWS_PER_WARP * dim_pad;
     for (int y0 = 0; y0 < ny; y0 += MT_Y_TILE) {
         __syncthreads();
@@ -72,7 +78,8 @@ bf_argmin_kernel(const float* __restrict__ A, int na, const float* __restrict__ 
             for (int k = 0; k < MT_ROWS_PER_WARP; k++) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-                if (acc[k] < best[k]) { best[k] = acc[k]; bidx[k] = y0 + r; }      // strict: first minimum wins
+                if (acc[k] < best[k]) { second[k] = best[k]; best[k] = acc[k]; bidx[k] = y0 + r; }      // strict: first minimum wins
+                else if (acc[k] < second[k]) second[k] = acc[k];
             }
         }
     }
@@ -80,18 +87,29 @@ bf_argmin_kernel(const float* __restrict__ A, int na, const float* __restrict__ 
 #pragma unroll
         for (int k = 0; k < MT_ROWS_PER_WARP; k++) {
             const int x = x0 + warp * MT_ROWS_PER_WARP + k;
-            if (x < nx) { idx_out[x] = bidx[k]; d2_out[x] = best[k]; }
+            if (x < nx) {
+                idx_out[x] = bidx[k];
+                d2_out[x] = best[k];
+                if (!rev && second_ab) second_ab[x] = second[k];
+            }
         }
     }
 }
 
 __global__ void bf_cross_kernel(const int32_t* __restrict__ idx_ab, const float* __restrict__ d2_ab,
-                                const int32_t* __restrict__ idx_ba, int na, int cross_check,
-                                int32_t* __restrict__ train_out, float* __restrict__ dist_out) {
+                                const int32_t* __restrict__ idx_ba, const float* __restrict__ second_ab, double max_ratio,
+                                int na, int cross_check, int32_t* __restrict__ train_out, float* __restrict__ dist_out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= na) return;
     const int j = idx_ab[i];
-    const bool keep = j >= 0 && (!cross_check || idx_ba[j] == i);
+    bool keep = j >= 0 && (!cross_check || idx_ba[j] == i);
+    if (keep && second_ab) {
+        // skimage: ratio = best / second_best in float64, second_best == 0 -> eps; with a single train descriptor
+        // there is no other candidate and the "second best" read back is the inf written over the best: ratio 0
+        double sb = sqrt((double)second_ab[i]);
+        if (sb == 0.0) sb = 2.220446049250313e-16;
+        keep = sqrt((double)d2_ab[i]) / sb < max_ratio;
+    }
     train_out[i] = keep ? j : -1;
     dist_out[i] = keep ? sqrtf(d2_ab[i]) : __int_as_float(0x7f800000);
 }
@@ -101,6 +119,7 @@ struct MatchWs {
     float* d2_ab;
     int32_t* idx_ba;
     float* d2_ba;
+    float* second_ab;
 };
 
 static void match_layout(MatchWs& w, Arena& a, int n1, int n2) {
@@ -108,6 +127,7 @@ static void match_layout(MatchWs& w, Arena& a, int n1, int n2) {
     w.d2_ab = a.take<float>((size_t)n1);
     w.idx_ba = a.take<int32_t>((size_t)n2);
     w.d2_ba = a.take<float>((size_t)n2);
+    w.second_ab = a.take<float>((size_t)n1);
 }
 
 }  // namespace r3d
@@ -122,10 +142,11 @@ extern "C" size_t r3d_match_workspace_bytes(int n1, int n2) {
     return a.used + 512;
 }
 
-extern "C" int r3d_match_descriptors(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
-                                     int32_t* train_idx_out, float* dist_out, void* workspace, size_t workspace_bytes,
-                                     void* stream) {
+static int match_run(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check, bool ratio_test,
+                     double max_ratio, int32_t* train_idx_out, float* dist_out, void* workspace, size_t workspace_bytes,
+                     void* stream) {
     if (!des1 || !des2 || !train_idx_out || !dist_out || n1 <= 0 || n2 <= 0 || dim <= 0) return R3D_ERR_INVALID;
+    if (ratio_test && !(max_ratio == max_ratio)) return R3D_ERR_INVALID;
     const int dim_pad = (dim + 31) / 32 * 32;
     const size_t smem = (size_t)(MT_X_TILE + MT_Y_TILE) * dim_pad * sizeof(float);
     if (smem > 200 * 1024) return R3D_ERR_INVALID;      // descriptors longer than ~1000 floats are not supported
@@ -136,9 +157,23 @@ extern "C" int r3d_match_descriptors(const float* des1, int n1, const float* des
     if (!a.ok) return R3D_ERR_WORKSPACE;
     if (smem > 48 * 1024) R3D_CUDA(cudaFuncSetAttribute(bf_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int nmax = n1 > n2 ? n1 : n2;
+    float* second = ratio_test ? w.second_ab : nullptr;
     R3D_LAUNCH(bf_argmin_kernel, dim3((nmax + MT_X_TILE - 1) / MT_X_TILE, 2), MT_THREADS, smem, st, des1, n1, des2, n2, dim,
-               dim_pad, w.idx_ab, w.d2_ab, w.idx_ba, w.d2_ba);
-    R3D_LAUNCH(bf_cross_kernel, (n1 + 255) / 256, 256, 0, st, w.idx_ab, w.d2_ab, w.idx_ba, n1, cross_check, train_idx_out,
-               dist_out);
+               dim_pad, w.idx_ab, w.d2_ab, w.idx_ba, w.d2_ba, second);
+    R3D_LAUNCH(bf_cross_kernel, (n1 + 255) / 256, 256, 0, st, w.idx_ab, w.d2_ab, w.idx_ba, (const float*)second, max_ratio, n1,
+               cross_check, train_idx_out, dist_out);
     return R3D_OK;
+}
+
+extern "C" int r3d_match_descriptors(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
+                                     int32_t* train_idx_out, float* dist_out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    return match_run(des1, n1, des2, n2, dim, cross_check, false, 1.0, train_idx_out, dist_out, workspace, workspace_bytes, stream);
+}
+
+extern "C" int r3d_match_descriptors_ratio(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
+                                           double max_ratio, int32_t* train_idx_out, float* dist_out, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+    return match_run(des1, n1, des2, n2, dim, cross_check, max_ratio < 1.0, max_ratio, train_idx_out, dist_out, workspace,
+                     workspace_bytes, stream);
 }

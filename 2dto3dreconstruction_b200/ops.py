@@ -91,6 +91,32 @@ def transform_points(points, T):
     return out
 
 
+def voxel_down_sample(xyz, voxel_size):
+    """K7: open3d voxel_down_sample on a CUDA (n,3) float64 tensor -> (m,3) tensor, voxels in ascending (z, y, x) order."""
+    C.require_device()
+    t = C.torch()
+    xyz = xyz.contiguous()
+    assert xyz.dtype == t.float64 and xyz.dim() == 2 and xyz.shape[1] == 3
+    n = xyz.shape[0]
+    if n == 0:
+        return xyz.clone()
+    if not (voxel_size > 0.0):
+        raise RuntimeError("[VoxelDownSample] voxel_size <= 0.")         # Open3D's message
+    out = t.empty_like(xyz)
+    meta = t.zeros(2, dtype=t.int32, device="cuda")                      # n_out, status
+    L = C.lib()
+    nws = L.r3d_voxel_downsample_workspace_bytes(n)
+    ws = C.workspace(nws)
+    C.check(L.r3d_voxel_downsample(C.ptr(xyz), n, float(voxel_size), C.ptr(out), C.ptr(meta[0:]), C.ptr(meta[1:]), C.ptr(ws), nws,
+                                   C.stream_ptr()), "r3d_voxel_downsample")
+    m, status = (int(v) for v in meta.cpu())
+    if status == 1:
+        raise RuntimeError("[VoxelDownSample] voxel_size is too small.")     # Open3D's message
+    if status == 2:
+        raise ValueError("voxel_down_sample: non-finite coordinate")
+    return out[:m]
+
+
 def pack_xyzw(xyz):
     """(n,3) float64 CUDA tensor -> (n,4) xyzw tensor (32-byte aligned rows)."""
     C.require_device()
@@ -192,8 +218,9 @@ def ransac3d_score(T, P, Q, thresh=10.0):
     return counts
 
 
-def match_descriptors(des1, des2, cross_check=True):
+def match_descriptors(des1, des2, cross_check=True, max_ratio=1.0):
     """K5: brute-force L2 matching of float32 descriptor sets (CUDA tensors [n1,dim], [n2,dim]).
+    max_ratio < 1 adds skimage's best / second-best ratio test (q8.py:90).
     Returns (train_idx int32 [n1] with -1 for unmatched queries, dist float32 [n1])."""
     C.require_device()
     t = C.torch()
@@ -207,8 +234,8 @@ def match_descriptors(des1, des2, cross_check=True):
     L = C.lib()
     nws = L.r3d_match_workspace_bytes(n1, n2)
     ws = C.workspace(nws)
-    C.check(L.r3d_match_descriptors(C.ptr(des1), n1, C.ptr(des2), n2, dim, 1 if cross_check else 0, C.ptr(train), C.ptr(dist),
-                                    C.ptr(ws), nws, C.stream_ptr()), "r3d_match_descriptors")
+    C.check(L.r3d_match_descriptors_ratio(C.ptr(des1), n1, C.ptr(des2), n2, dim, 1 if cross_check else 0, float(max_ratio),
+                                          C.ptr(train), C.ptr(dist), C.ptr(ws), nws, C.stream_ptr()), "r3d_match_descriptors_ratio")
     return train, dist
 
 

@@ -3,6 +3,11 @@
     depth_images_to_3d_pts(depth_images, scale=1.)   reconstruct.py:336-344
     depth_images_to_3d_pts_ld(depth_images)          reconstruct.py:347-354
     chain_prefix(transformations)                    reconstruct.py:201-204 (prefix product only)
+    voxel_down_sample(points, voxel_size)            open3d PointCloud.voxel_down_sample as used at reconstruct.py:220
+    merge_point_clouds(point_clouds, transformations, voxel_size=2)
+                                                     reconstruct.py:201-220, the merge loop of chain_transformation on
+                                                     plain (N,3) arrays (the Open3D objects, normals and meshing that
+                                                     follow it are outside the path)
 
 The reference maps depth_to_voxel over the frames in a Python list comprehension; here all frames
 go through ONE K1 launch and the result is split into the same list of (N_f,3) arrays.
@@ -60,3 +65,34 @@ def chain_prefix(transformations):
     for t in transformations[1:]:
         out.append(np.dot(t, out[-1]))
     return out
+
+
+def voxel_down_sample(points, voxel_size):
+    """open3d.geometry.PointCloud.voxel_down_sample(voxel_size) on an (N,3) array (K7, csrc/voxel.cu): one point per
+    occupied voxel, the mean of its points; voxels in ascending (z, y, x) order (Open3D's order is unspecified)."""
+    C.require_device()
+    t = C.torch()
+    pts = np.ascontiguousarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[1] != 3:
+        raise ValueError("expected an (N,3) array")
+    return ops.voxel_down_sample(t.from_numpy(pts).cuda(), float(voxel_size)).cpu().numpy()
+
+
+def merge_point_clouds(point_clouds, transformations, voxel_size=2):
+    """The merge loop of chain_transformation (reconstruct.py:201-220): transformations[i] maps cloud i+1 (after the
+    prefix product) onto cloud 0's frame; every cloud is transformed, appended to the running cloud, and the running
+    cloud is voxel-down-sampled -- all on the device, one count read back per merge.  Returns the merged (N,3) array."""
+    C.require_device()
+    t = C.torch()
+    if len(transformations) != len(point_clouds) - 1:
+        raise ValueError("need one transformation per consecutive pair of clouds")
+    pre = chain_prefix(transformations) if len(transformations) else []
+    combined = t.from_numpy(np.ascontiguousarray(point_clouds[0], dtype=np.float64)).cuda()
+    for i in range(1, len(point_clouds)):
+        T = np.ascontiguousarray(pre[i - 1], dtype=np.float64)
+        if T.shape != (4, 4) or not np.array_equal(T[3], [0.0, 0.0, 0.0, 1.0]):
+            raise ValueError("transformations must be 4x4 with last row [0,0,0,1]")      # Open3D would divide by w
+        cloud = t.from_numpy(np.ascontiguousarray(point_clouds[i], dtype=np.float64)).cuda()
+        moved = ops.transform_points(cloud, t.from_numpy(T).cuda())
+        combined = ops.voxel_down_sample(t.cat((combined, moved), dim=0), float(voxel_size))
+    return combined.cpu().numpy()

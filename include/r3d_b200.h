@@ -200,6 +200,28 @@ size_t r3d_match_workspace_bytes(int n1, int n2);
 int r3d_match_descriptors(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
                           int32_t* train_idx_out, float* dist_out,
                           void* workspace, size_t workspace_bytes, void* stream);
+/*   ... with the second-best ratio test of skimage.feature.match_descriptors(des1, des2, max_ratio=0.8,
+ *   cross_check=True) as called at utils/homography_utils/q8.py:90 (scikit-image 0.17.2, not vendored): after the
+ *   mutual check a query is kept iff best / second_best < max_ratio (float64 distances; second_best = nearest OTHER
+ *   train descriptor, 0 replaced by DBL_EPSILON).  max_ratio >= 1 disables the test, as in skimage. */
+int r3d_match_descriptors_ratio(const float* des1, int n1, const float* des2, int n2, int dim, int cross_check,
+                                double max_ratio, int32_t* train_idx_out, float* dist_out,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * K7  voxel down-sampling of a (merged) cloud (the step right after registration)
+ *   replaces open3d.geometry.PointCloud.voxel_down_sample(voxel_size) as called in the merge loop of
+ *   chain_transformation, reconstruct.py:212-220 (Open3D is a third-party dependency of the reference, not vendored):
+ *   min_bound = min(points) - voxel_size/2; voxel = floor((p - min_bound) / voxel_size); one output point per occupied
+ *   voxel = mean of its points, summed in ascending index order.  Output order: ascending (z, y, x) voxel index
+ *   (Open3D's is the iteration order of an unordered_map, i.e. unspecified).
+ *   xyz: [n, 3] float64 packed (device); xyz_out: [<= n, 3]; n_out: int32 (device) number of voxels;
+ *   status_out (device, optional): 0 ok, 1 = voxel_size too small for the extent (Open3D raises), 2 = a non-finite
+ *   coordinate; n_out = 0 in both cases.  The transform of the merge step is r3d_transform_points.
+ * ------------------------------------------------------------------------------------ */
+size_t r3d_voxel_downsample_workspace_bytes(int64_t n);
+int r3d_voxel_downsample(const double* xyz, int64_t n, double voxel_size, double* xyz_out, int32_t* n_out,
+                         int32_t* status_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Fused registration of depth-frame pairs: K1 on both frames, grid build, ICP.

@@ -466,6 +466,34 @@ def match_descriptors(des1, des2):
     return q, q2t[q], np.sqrt(D2[q, q2t[q]]).astype(np.float32)
 
 
+def match_descriptors_skimage(des1, des2, max_ratio=0.8, cross_check=True):
+    """skimage.feature.match_descriptors(des1, des2, max_ratio=..., cross_check=...) as the reference calls it at
+    utils/homography_utils/q8.py:90 (scikit-image 0.17.2, requirements.txt:94 -- a third-party dependency that is neither
+    vendored nor installed here, so this restates its published algorithm, skimage/feature/match.py; PARITY UNPINNED
+    against the package itself).  Returns the (K, 2) int64 array of (index1, index2)."""
+    d1 = np.asarray(des1, dtype=np.float64)
+    d2 = np.asarray(des2, dtype=np.float64)
+    distances = np.empty((d1.shape[0], d2.shape[0]))
+    for s in range(0, d1.shape[0], 256):                     # = scipy cdist(..., 'euclidean')
+        diff = d1[s:s + 256, None, :] - d2[None, :, :]
+        distances[s:s + 256] = np.sqrt((diff * diff).sum(axis=2))
+    indices1 = np.arange(d1.shape[0])
+    indices2 = np.argmin(distances, axis=1)
+    if cross_check:
+        matches1 = np.argmin(distances, axis=0)
+        mask = indices1 == matches1[indices2]
+        indices1, indices2 = indices1[mask], indices2[mask]
+    if max_ratio < 1.0:
+        best = distances[indices1, indices2]
+        distances[indices1, indices2] = np.inf
+        second_idx = np.argmin(distances[indices1], axis=1)
+        second = distances[indices1, second_idx]
+        second[second == 0] = np.finfo(np.double).eps
+        mask = best / second < max_ratio
+        indices1, indices2 = indices1[mask], indices2[mask]
+    return np.column_stack((indices1, indices2)).astype(np.int64)
+
+
 # --------------------------------------------------------------------------------------
 # Chaining prefix product  (reconstruct.py:201-204)
 # --------------------------------------------------------------------------------------
@@ -475,6 +503,44 @@ def chain_prefix(transformations):
     for t in transformations[1:]:
         out.append(np.dot(t, out[-1]))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# Merge + voxel down-sample  (reconstruct.py:201-220).  open3d 0.9.0 (requirements.txt) is a third-party
+# dependency that is neither vendored nor installed here: PointCloud::Transform and PointCloud::VoxelDownSample
+# are restated from their published source -- PARITY UNPINNED against the package itself.  Open3D emits the
+# voxels in unordered_map order (unspecified); this restatement emits them in ascending (z, y, x) voxel order.
+# --------------------------------------------------------------------------------------
+
+def voxel_down_sample(points, voxel_size):
+    pts = np.asarray(points, dtype=np.float64)
+    if voxel_size <= 0.0:
+        raise RuntimeError("[VoxelDownSample] voxel_size <= 0.")
+    if len(pts) == 0:
+        return pts.copy()
+    min_bound = pts.min(axis=0) - voxel_size * 0.5
+    max_bound = pts.max(axis=0) + voxel_size * 0.5
+    if voxel_size * np.iinfo(np.int32).max < (max_bound - min_bound).max():
+        raise RuntimeError("[VoxelDownSample] voxel_size is too small.")
+    vox = np.floor((pts - min_bound) / voxel_size).astype(np.int64)
+    order = np.lexsort((vox[:, 0], vox[:, 1], vox[:, 2]))               # stable: index order inside a voxel
+    sv = vox[order]
+    head = np.ones(len(pts), dtype=bool)
+    head[1:] = np.any(sv[1:] != sv[:-1], axis=1)
+    vid = np.cumsum(head) - 1
+    sums = np.zeros((int(vid[-1]) + 1, 3))
+    np.add.at(sums, vid, pts[order])                                    # unbuffered: sequential accumulation in index order
+    counts = np.bincount(vid).astype(np.float64)
+    return sums / counts[:, None]
+
+
+def merge_point_clouds(point_clouds, transformations, voxel_size=2):
+    pre = chain_prefix(transformations) if len(transformations) else []
+    combined = np.asarray(point_clouds[0], dtype=np.float64)
+    for i in range(1, len(point_clouds)):
+        moved = get_transformed_points(np.asarray(point_clouds[i], dtype=np.float64), pre[i - 1])
+        combined = voxel_down_sample(np.vstack((combined, moved)), voxel_size)
+    return combined
 
 
 # --------------------------------------------------------------------------------------

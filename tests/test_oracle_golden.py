@@ -190,3 +190,24 @@ def test_match_descriptors_vs_cv2():
         q, t, d = O.match_descriptors(d1, d2)
         assert np.array_equal(np.stack((q, t), axis=1), np.array([(x.queryIdx, x.trainIdx) for x in m]).reshape(-1, 2))
         assert np.array_equal(d, np.array([x.distance for x in m], dtype=np.float32))
+
+
+def test_voxel_down_sample_hand_example():
+    """Open3D's published algorithm on a case small enough to do by hand: min = (0,0,0), voxel 2 -> min_bound = -1;
+    voxel(p) = floor((p + 1) / 2)."""
+    pts = np.array([[0.0, 0.0, 0.0], [0.9, 0.5, 0.2], [1.0, 0.0, 0.0], [2.5, 0.0, 0.0], [0.0, 0.0, 3.0], [0.5, 0.5, 0.5]])
+    out = O.voxel_down_sample(pts, 2.0)
+    # voxels: (0,0,0) <- points 0, 1, 5; (1,0,0) <- points 2, 3; (0,0,2) <- point 4; output in (z, y, x) order
+    want = np.array([[(0.0 + 0.9 + 0.5) / 3, (0.0 + 0.5 + 0.5) / 3, (0.0 + 0.2 + 0.5) / 3], [(1.0 + 2.5) / 2, 0.0, 0.0], [0.0, 0.0, 3.0]])
+    assert np.array_equal(out, want)
+
+
+def test_skimage_match_restatement_hand_example():
+    """q8.py:90 semantics on a 3x3 case: mutual nearest neighbours, then best / second-best < max_ratio."""
+    d1 = np.array([[0.0, 0.0], [10.0, 0.0], [0.0, 10.0]], dtype=np.float32)
+    d2 = np.array([[1.0, 0.0], [10.0, 1.0], [5.0, 7.0]], dtype=np.float32)
+    # distances: row0 = [1, 10.05, 8.60]; row1 = [9, 1, 8.60]; row2 = [10.05, 13.45, 5.83]
+    assert np.array_equal(O.match_descriptors_skimage(d1, d2, max_ratio=1.0, cross_check=True), [[0, 0], [1, 1], [2, 2]])
+    # ratios: 1/8.60 = 0.116, 1/8.60 = 0.116, 5.83/10.05 = 0.580
+    assert np.array_equal(O.match_descriptors_skimage(d1, d2, max_ratio=0.5, cross_check=True), [[0, 0], [1, 1]])
+    assert np.array_equal(O.match_descriptors_skimage(d1, d2, max_ratio=0.8, cross_check=True), [[0, 0], [1, 1], [2, 2]])
