@@ -22,7 +22,10 @@
 namespace r3d {
 
 constexpr int NN_THREADS = 128;
-constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent nn kernel (see nn_kernel)
+constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent nn kernel (see nn_kernel) ...
+constexpr int NN_VWARPS_BIG = 8192;  // ... and for a pair of more than NN_VWARPS_BIG_FROM source points: a single large pair must
+constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A function of the pair alone, so batching stays irrelevant.
+__host__ __device__ __forceinline__ int vwarps_for(int n_src) { return n_src > NN_VWARPS_BIG_FROM ? NN_VWARPS_BIG : NN_VWARPS; }
 
 struct PairState {
     double T[12];        // cumulative transform, rows 0..2 of the 4x4
@@ -80,7 +83,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
     w.src_rows = w.src_tiles * (NN_THREADS / 32);
-    if (w.src_rows < NN_VWARPS) w.src_rows = NN_VWARPS;
+    if (w.src_rows < vwarps_for(max_src)) w.src_rows = vwarps_for(max_src);
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
     w.src_desc = a.take<SortDesc>(P);
@@ -106,7 +109,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
         int per_pair = (148 * 8 + n_pairs - 1) / n_pairs;
         const int cap = (max_src + NN_THREADS - 1) / NN_THREADS;
         if (per_pair > cap) per_pair = cap;
-        if (per_pair > NN_VWARPS / (NN_THREADS / 32)) per_pair = NN_VWARPS / (NN_THREADS / 32);
+        if (per_pair > vwarps_for(max_src) / (NN_THREADS / 32)) per_pair = vwarps_for(max_src) / (NN_THREADS / 32);
         if (per_pair < 1) per_pair = 1;
         w.nn_ctas = per_pair;
     }
@@ -470,7 +473,8 @@ nn_kernel(IcpWorkspace w, int write_d2) {
     int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
     const int n_tasks = (s_ngrp + NGW - 1) / NGW;
-    // Work is dealt to NN_VWARPS "virtual warps" per pair (virtual warp u owns tasks u, u + NN_VWARPS, ...)
+    const int nvw = vwarps_for(w.state[pair].n_src);
+    // Work is dealt to vwarps_for(n_src) "virtual warps" per pair (virtual warp u owns tasks u, u + nvw, ...)
     // and each physical warp runs some of them back to back.  The moment sums are kept per VIRTUAL warp,
     // so their summation order -- and therefore every bit of the result -- does not depend on how many
     // CTAs this launch happened to get (chunk size, number of pairs in flight, GPU count).
@@ -480,9 +484,9 @@ nn_kernel(IcpWorkspace w, int write_d2) {
     int vw = 0;
     if (lane == 0) vw = atomicAdd(vw_counter, 1);
     vw = __shfl_sync(0xffffffffu, vw, 0);
-    if (vw >= NN_VWARPS) break;
+    if (vw >= nvw) break;
     double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
-    for (int task = vw; task < n_tasks; task += NN_VWARPS) {
+    for (int task = vw; task < n_tasks; task += nvw) {
         const int gid = task * NGW + lane / G;
         bool active = false;
         int i = 0;
@@ -523,7 +527,7 @@ nn_kernel(IcpWorkspace w, int write_d2) {
             acc += warp_reduce16(m, reinterpret_cast<double*>(stage[warp]));
         }
     }
-    // every virtual warp writes its row (zeros if it had no task): solve_kernel sums NN_VWARPS rows
+    // every virtual warp writes its row (zeros if it had no task): solve_kernel sums vwarps_for(n_src) rows
     if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
     }
 }
@@ -582,6 +586,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
     const int n_tasks = (s_n + 31) >> 5;
+    const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
     list_init(lists[warp], v.pts);
@@ -598,9 +603,9 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         int vw = 0;
         if (lane == 0) vw = atomicAdd(vw_counter, 1);
         vw = __shfl_sync(0xffffffffu, vw, 0);
-        if (vw >= NN_VWARPS) break;
+        if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
-        for (int task = vw; task < n_tasks; task += NN_VWARPS) {
+        for (int task = vw; task < n_tasks; task += nvw) {
             const int i = task * 32 + lane;
             const bool active = i < s_n;
             double qx = 0.0, qy = 0.0, qz = 0.0;
@@ -889,7 +894,7 @@ solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     __shared__ double m[16];
     const int n = st->n_src;
     // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? rows_fixed : (n + 31) / 32;
+    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32;
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -1131,7 +1136,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
             }
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
         }
-        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? NN_VWARPS : 0);
+        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
     }
     R3D_LAUNCH(final_kernel, (P + 63) / 64, 64, 0, st, w, T_out, iters_out, mean_err_out);
     if ((last_idx || last_dist || last_keep) && prm.max_iterations > 0) {

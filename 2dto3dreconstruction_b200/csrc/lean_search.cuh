@@ -437,9 +437,12 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
         const bool whole = lox == 0 && loy == 0 && loz == 0 && hix == g.nx - 1 && hiy == g.ny - 1 && hiz == g.nz - 1;
         const long long nseg = (long long)(hiy - loy + 1) * (hiz - loz + 1) * ((hix >> 2) - (lox >> 2) + 1);
         const long long nblk = (long long)((hiy >> 2) - (loy >> 2) + 1) * ((hiz >> 2) - (loz >> 2) + 1) * ((hix >> 2) - (lox >> 2) + 1);
-        // small boxes are walked row by row, larger ones block by block; boxes of more than LEAN_BLOCKS_MAX blocks are
-        // searched one query at a time with distance pruning
-        if (nseg <= (long long)LEAN_ROW_SEGS_MAX || nblk <= (long long)LEAN_BLOCKS_MAX) {
+        // small boxes are walked row by row, larger ones block by block.  A box of more than LEAN_BLOCKS_MAX block slots
+        // that is also a large part of the cloud (more than an eighth of its occupied blocks: a small cloud with far
+        // outliers, a badly misaligned pair) is searched one query at a time by sweeping the cloud's block list with
+        // distance pruning; in a large cloud the same number of slots is a small neighbourhood and is still walked
+        // (the sweep costs n_blocks / 32 steps per query, the walk nblk / 32 lookups per warp).
+        if (nseg <= (long long)LEAN_ROW_SEGS_MAX || nblk <= max((long long)LEAN_BLOCKS_MAX, (long long)(g.n_blocks >> 3))) {
             // the union of the served balls' bounding boxes in world coordinates: a point outside it is
             // outside every served ball.  When the box is the whole grid everything is looked at once and
             // the answer is final for every lane, so nothing may be filtered.

@@ -202,4 +202,78 @@ ms = timed(k4a, flush=False)
 out["K4A_ransac2d"] = {"what": "q9.ransac_loop scoring body: 100 hypotheses x 1100 keypoints, 480x640 bins", "ms": ms,
                        "hypotheses_per_s": 100 / ms * 1e3, "note": "the reference needs ~65 ms per hypothesis (SURVEY.md section 6)"}
 
+# ---- K5: descriptor matching at the kitchen size (1100 x 1200 SIFT descriptors), with and without the ratio test ------
+d1 = torch.randint(0, 256, (1100, 128), device=dev, generator=g).float()
+d2 = torch.randint(0, 256, (1200, 128), device=dev, generator=g).float()
+mws = L.r3d_match_workspace_bytes(1100, 1200)
+wsm = C.workspace(mws)
+tr = torch.empty(1100, dtype=torch.int32, device=dev)
+di = torch.empty(1100, dtype=torch.float32, device=dev)
+
+
+def k5():
+    C.check(L.r3d_match_descriptors_ratio(C.ptr(d1), 1100, C.ptr(d2), 1200, 128, 1, 0.8, C.ptr(tr), C.ptr(di), C.ptr(wsm), mws, st))
+
+
+ms = timed(k5, flush=False)
+out["K5_match_descriptors"] = {"what": "1100 x 1200 x 128 float32, both directions + cross-check + ratio test", "ms": ms,
+                               "gflops": 2 * 3 * 1100 * 1200 * 128 / ms / 1e6}
+
+# ---- K7: voxel down-sampling of a 2 M point merged cloud (voxel 2) ------------------------------------------------------
+nv = 2_000_000
+u = torch.rand(nv, dtype=torch.float64, device=dev, generator=g) * 640
+v = torch.rand(nv, dtype=torch.float64, device=dev, generator=g) * 480
+cloud = torch.stack(((u - 319.5) * 3.8, (v - 239.5) * 3.8, 2000 + 600 * torch.sin(u / 97)), dim=1).contiguous()
+vws = L.r3d_voxel_downsample_workspace_bytes(nv)
+wsv = C.workspace(vws)
+vout = torch.empty_like(cloud)
+meta = torch.zeros(2, dtype=torch.int32, device=dev)
+
+
+def k7():
+    C.check(L.r3d_voxel_downsample(C.ptr(cloud), nv, 2.0, C.ptr(vout), C.ptr(meta[0:]), C.ptr(meta[1:]), C.ptr(wsv), vws, st))
+
+
+ms = timed(k7)
+nvox = int(meta[0].item())
+passes = 6          # 2 radix passes per axis at this extent
+algo = nv * (24 + 12) + passes * nv * 16 + nv * (4 + 12 + 24) + nvox * 24
+out["K7_voxel_downsample"] = {"what": "2 M points, voxel 2 -> %d voxels (bbox, coords, 3 stable sorts, heads, scan, reduce)" % nvox,
+                              "ms": ms, "points_per_s": nv / ms * 1e3, "algorithmic_bytes": algo, "achieved_gbs": algo / ms / 1e6,
+                              "frac_of_hbm": algo / ms / 1e6 / HBM}
+
+# ---- configs[3]: one 2 M x 2 M pair, 30 iterations (single GPU; SURVEY 8e: replicas only) --------------------------------
+icp_mod = importlib.import_module("2dto3dreconstruction_b200.utils.icp")
+from oracle import ref_port as O  # noqa: E402  (input generation only)
+if True:
+    fa2, _ = O.synth_depth_pair(0, h=1226, w=1632, seed_base=7)          # SURVEY 8d C4, as tests/test_gpu_full_size.py
+    A2 = O.depth_to_voxel_ld(fa2)
+    ang = np.deg2rad(2.0)
+    Tt = np.eye(4)
+    Tt[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    Tt[:3, 3] = [15.0, -8.0, 5.0]
+    B2 = O.get_transformed_points(A2, Tt) + np.random.default_rng(7).normal(0.0, 0.5, size=A2.shape)
+    a4 = ops.pack_xyzw(C.to_device(np.ascontiguousarray(A2)))
+    b4 = ops.pack_xyzw(C.to_device(np.ascontiguousarray(B2)))
+    oa = torch.tensor([0, len(A2)], dtype=torch.int32, device=dev)
+    ob = torch.tensor([0, len(B2)], dtype=torch.int32, device=dev)
+    bws = L.r3d_icp_workspace_bytes(1, len(A2), len(B2))
+    wsb = C.workspace(bws)
+    prm = C.IcpParams(30, 0, 0.0, 1.0, 0.0)
+    Tb = torch.empty((1, 16), dtype=torch.float64, device=dev)
+    itb = torch.empty(1, dtype=torch.int32, device=dev)
+    eb = torch.empty(1, dtype=torch.float64, device=dev)
+
+    def big_icp():
+        C.check(L.r3d_icp_batch(C.ptr(a4), C.ptr(oa), C.ptr(b4), C.ptr(ob), 1, len(A2), len(B2), None, ctypes.byref(prm), C.ptr(Tb),
+                                C.ptr(itb), C.ptr(eb), None, None, None, C.ptr(wsb), bws, st))
+
+    L.r3d_nn_timing_enable(1)
+    ms = timed(big_icp)
+    L.r3d_nn_timing_read(ctypes.byref(tms), ctypes.byref(tn), ctypes.byref(tq), 1)
+    L.r3d_nn_timing_enable(0)
+    out["configs3_single_pair_2M"] = {"what": "r3d_icp_batch on one %d x %d pair, 30 iterations, tolerance 0 (grid build + source sort + loop)" % (len(A2), len(B2)),
+                                      "ms": ms, "correspondences_per_s": 30 * len(A2) / ms * 1e3,
+                                      "nn_kernel_ms_per_launch": tms.value / max(tn.value, 1), "mean_err": float(eb.item())}
+
 print(json.dumps(out, indent=1))
