@@ -75,6 +75,7 @@ SIGNATURES = {
     "r3d_nn_timing_enable": (None, [c_int]),
     "r3d_nn_timing_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), c_int]),
     "r3d_nn_stats_read": (c_int, [ctypes.POINTER(ctypes.c_uint64), c_int]),
+    "r3d_nn_stats_read_ext": (c_int, [ctypes.POINTER(ctypes.c_uint64), c_int]),
 }
 
 _lib = None

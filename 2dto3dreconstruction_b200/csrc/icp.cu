@@ -25,6 +25,13 @@ constexpr int NN_THREADS = 128;
 constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent nn kernel (see nn_kernel) ...
 constexpr int NN_VWARPS_BIG = 8192;  // ... and for a pair of more than NN_VWARPS_BIG_FROM source points: a single large pair must
 constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A function of the pair alone, so batching stays irrelevant.
+// Queries per task of the lean kernel: a warp normally takes 32 consecutive queries; a SMALL pair (the reference's
+// own sizes: 13k-26k points after its sub-sampling) would then give a few hundred warps, one per SM sub-partition,
+// each running its whole search serially.  Such pairs use 8 queries per task, every query on four lanes that each
+// evaluate a quarter of the candidates: four times the warps, a quarter of the per-task serial work.  Also a
+// function of the pair alone.
+constexpr int NN_SMALL_PAIR = 1 << 15;
+__host__ __device__ __forceinline__ int queries_per_task(int n_src) { return n_src <= NN_SMALL_PAIR ? 8 : 32; }
 __host__ __device__ __forceinline__ int vwarps_for(int n_src) { return n_src > NN_VWARPS_BIG_FROM ? NN_VWARPS_BIG : NN_VWARPS; }
 
 struct PairState {
@@ -105,9 +112,10 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.vw_counter = a.take<int>(P);
     {
         // persistent nn kernel: enough CTAs to fill 148 SMs x 8 resident CTAs over the chunk's pairs,
-        // never more than one warp per 32 queries
+        // never more than one warp per task (32 queries; 8 for small pairs)
         int per_pair = (148 * 8 + n_pairs - 1) / n_pairs;
-        const int cap = (max_src + NN_THREADS - 1) / NN_THREADS;
+        const int per_cta = queries_per_task(max_src) * (NN_THREADS / 32);
+        const int cap = (max_src + per_cta - 1) / per_cta;
         if (per_pair > cap) per_pair = cap;
         if (per_pair > vwarps_for(max_src) / (NN_THREADS / 32)) per_pair = vwarps_for(max_src) / (NN_THREADS / 32);
         if (per_pair < 1) per_pair = 1;
@@ -585,7 +593,8 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
     float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
-    const int n_tasks = (s_n + 31) >> 5;
+    const int qpt = queries_per_task(s_n);
+    const int n_tasks = (s_n + qpt - 1) / qpt;
     const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
@@ -606,8 +615,9 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
         for (int task = vw; task < n_tasks; task += nvw) {
-            const int i = task * 32 + lane;
+            const int i = task * qpt + (lane & (qpt - 1));      // qpt = 8: four lanes per query (lean_search)
             const bool active = i < s_n;
+            const bool primary = lane < qpt;                    // the replica that writes the results
             double qx = 0.0, qy = 0.0, qz = 0.0;
             Best seed, other;
             seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
@@ -635,16 +645,23 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 }
             }
             R3D_STAT(0, 1);
+#ifdef R3D_NN_STATS
+            const long long t_task = clock64();
+#endif
             float cover = 0.0f;
-            lean_search(lists[warp], tma_phase, seed, other, v, g, active && !skip, qx, qy, qz, slack, cover);
+            lean_search(lists[warp], tma_phase, seed, other, v, g, active && !skip, qx, qy, qz, slack, cover, qpt);
             const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
 #ifdef R3D_NN_STATS
-            R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip)));
+            R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip && primary)));
             // a skipped lane still evaluates the warp's candidates: none of them may beat its seed
             R3D_STAT(7, __popc(__ballot_sync(0xffffffffu, active && skip && (other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx)))));
 #endif
+#ifdef R3D_NN_STATS
+            R3D_STAT(12, clock64() - t_task);
+            R3D_STAT_MAX(13, clock64() - t_task);
+#endif
             const Best best = seed_wins ? seed : other;
-            if (active) {
+            if (active && primary) {
                 nn_pos[i] = best.pos;
                 if (!FUSED || write_d2) d2_out[i] = best.d2;
                 float nb = 0.0f;
@@ -661,7 +678,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 double m[16];
 #pragma unroll
                 for (int k = 0; k < 16; k++) m[k] = 0.0;
-                if (active) {
+                if (active && primary) {
                     const Point4 b = load_point(v.pts + best.pos);
                     accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
                                     b.z - g.shift[2], sqrt(best.d2));
@@ -1240,23 +1257,26 @@ extern "C" int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* 
     return R3D_OK;
 }
 
-extern "C" int r3d_nn_stats_read(uint64_t* out8_host, int reset) {
+static int nn_stats_read(uint64_t* out_host, int n, int reset) {
 #ifdef R3D_NN_STATS
-    if (out8_host) {
-        cudaError_t e = cudaMemcpyFromSymbol(out8_host, g_nn_stats, 8 * sizeof(unsigned long long));
+    if (out_host) {
+        cudaError_t e = cudaMemcpyFromSymbol(out_host, g_nn_stats, (size_t)n * sizeof(unsigned long long));
         if (e != cudaSuccess) { set_cuda_error(e, "nn stats"); return R3D_ERR_CUDA; }
     }
     if (reset) {
-        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         cudaError_t e = cudaMemcpyToSymbol(g_nn_stats, z, sizeof(z));
         if (e != cudaSuccess) { set_cuda_error(e, "nn stats"); return R3D_ERR_CUDA; }
     }
     return R3D_OK;
 #else
-    (void)out8_host; (void)reset;
+    (void)out_host; (void)n; (void)reset;
     return R3D_ERR_INVALID;      // the library was built without -DR3D_NN_STATS
 #endif
 }
+
+extern "C" int r3d_nn_stats_read(uint64_t* out8_host, int reset) { return nn_stats_read(out8_host, 8, reset); }
+extern "C" int r3d_nn_stats_read_ext(uint64_t* out16_host, int reset) { return nn_stats_read(out16_host, 16, reset); }
 
 extern "C" int r3d_set_option(int option, double value) {
     switch (option) {

@@ -65,8 +65,15 @@ constexpr unsigned FULL = 0xffffffffu;
 //   0 tasks  1 search rounds  2 candidate evaluations per lane  3 lanes whose search was skipped
 //   4 segment lookup rounds   5 segments looked up              6 non-empty segments
 //   7 skipped lanes whose seed was beaten by an evaluated point (a violated bound: must stay 0)
+//   8 single-query (far) searches  9 their block-list sweep steps  10 their 32-point scan steps  11 block-granular walks
+//   12 sum of task durations (clock64)  13 longest task (clock64)          (8..13: r3d_nn_stats_read_ext)
 #ifdef R3D_NN_STATS
-static __device__ unsigned long long g_nn_stats[8];      // this header is included by icp.cu only
+static __device__ unsigned long long g_nn_stats[16];     // this header is included by icp.cu only
+#define R3D_STAT_MAX(slot, n)                                                               \
+    do {                                                                                    \
+        const unsigned long long _v = (unsigned long long)(n);                              \
+        if ((threadIdx.x & 31) == 0) atomicMax(&g_nn_stats[slot], _v);                      \
+    } while (0)
 #define R3D_STAT(slot, n)                                                                   \
     do {                                                                                    \
         const unsigned long long _v = (unsigned long long)(n); /* evaluated by every lane */ \
@@ -74,6 +81,7 @@ static __device__ unsigned long long g_nn_stats[8];      // this header is inclu
     } while (0)
 #else
 #define R3D_STAT(slot, n) do { } while (0)
+#define R3D_STAT_MAX(slot, n) do { } while (0)
 #endif
 
 // one candidate of the list: xy = (x, y), zw = (z, cloud index | sorted position << 32).
@@ -99,6 +107,7 @@ struct WarpList {
     double2* sxy;      // [LEAN_LIST_CAP] (x, y)
     double2* szw;      // [LEAN_LIST_CAP] (z, tag)
     int n;             // warp-uniform
+    int nrep, rep;     // small pairs: every query sits on nrep = 4 lanes (replica rep = lane / 8), else nrep = 1, rep = 0
     double lo[3], hi[3];      // filter box (world coordinates)
 #if R3D_LEAN_TMA
     const double2* stage;     // two staging buffers of 32 raw 32-byte records each, filled by cp.async.bulk
@@ -114,6 +123,18 @@ __device__ __forceinline__ void list_flush(WarpList& L, Best& best, int seed_pos
     __syncwarp();
     const int n = L.n;
     R3D_STAT(2, (n + 3) & ~3);
+    if (L.nrep > 1) {
+        // replica r of a query takes entries r, r + 4, ...: a quarter of the scan each (lean_scan_box merges them)
+#pragma unroll 1
+        for (int u = L.rep; u < n; u += 8) {
+            const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + 4], b1 = L.szw[u + 4];
+            eval_staged(best, seed_pos, a0, b0, qx, qy, qz);
+            eval_staged(best, seed_pos, a1, b1, qx, qy, qz);
+        }
+        __syncwarp();
+        L.n = 0;
+        return;
+    }
 #pragma unroll 1
     for (int u = 0; u < n; u += 4) {
         const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + 1], b1 = L.szw[u + 1];
@@ -156,6 +177,7 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
     const int by0 = loy >> 2, nby = (hiy >> 2) - by0 + 1, bz0 = loz >> 2, nbz = (hiz >> 2) - bz0 + 1;
     const int nblk = nxb * nby * nbz;
     const bool by_block = nseg > LEAN_ROW_SEGS_MAX;      // warp-uniform
+    R3D_STAT(11, by_block ? 1 : 0);
     const int n_units = by_block ? nblk : nseg;
     // exact for the small integers involved (a few hundred units): quotient by reciprocal, then fix up
     const int d0 = nxb, d1 = by_block ? nby : ny;
@@ -275,6 +297,16 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
 #endif
     }
     if (L.n > 0) list_flush(L, best, seed_pos, qx, qy, qz);
+    if (L.nrep > 1) {
+        // the four replicas of a query have each seen a quarter of the candidates: give all of them the minimum, so
+        // that they keep taking the same decisions
+#pragma unroll
+        for (int o = 8; o <= 16; o <<= 1) {
+            const double od2 = __shfl_xor_sync(FULL, best.d2, o);
+            const int oidx = __shfl_xor_sync(FULL, best.idx, o), opos = __shfl_xor_sync(FULL, best.pos, o);
+            if (od2 < best.d2 || (od2 == best.d2 && oidx < best.idx)) { best.d2 = od2; best.idx = oidx; best.pos = opos; }
+        }
+    }
 }
 
 // Exact NN for the warp's 32 queries.
@@ -321,7 +353,9 @@ __device__ __forceinline__ Best far_query_search(int owner, const Best& seed, co
     Best loc;
     loc.d2 = CUDART_INF; loc.idx = 0x7fffffff; loc.pos = -1;
     bool all = true;
+    R3D_STAT(8, 1);
     for (int b0 = 0; b0 < g.n_blocks; b0 += 32) {
+        R3D_STAT(9, 1);
         const int b = b0 + lane;
         bool hit = false;
         if (b < g.n_blocks) {
@@ -339,9 +373,14 @@ __device__ __forceinline__ Best far_query_search(int owner, const Best& seed, co
         const int in_range = min(32, g.n_blocks - b0);
         all = all && (__popc(m) == in_range);
         while (m) {
+            // a run of consecutive hit blocks is one contiguous range of the sorted cloud (a block holds ~10 points:
+            // scanned one block at a time most lanes would idle)
             const int j = __ffs(m) - 1;
-            m &= m - 1u;
-            const uint32_t s0 = __ldg(v.block_first + b0 + j), e0 = __ldg(v.block_first + b0 + j + 1);
+            const unsigned rest = ~(m >> j);
+            const int len = rest ? __ffs(rest) - 1 : 32;
+            m = (j + len >= 32) ? 0u : (m >> (j + len)) << (j + len);
+            const uint32_t s0 = __ldg(v.block_first + b0 + j), e0 = __ldg(v.block_first + b0 + j + len);
+            R3D_STAT(10, (e0 - s0 + 31) / 32);
             for (uint32_t k = s0 + (uint32_t)lane; k < e0; k += 32) {
                 const double2* p = reinterpret_cast<const double2*>(v.pts + k);
                 const double2 xy = __ldg(p), zw = __ldg(p + 1);
@@ -377,7 +416,7 @@ __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2
 
 __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, const Best& seed, Best& other, const GridView& v,
                                             const GridParams& g, bool active, double qx, double qy, double qz, float slack,
-                                            float& cover) {
+                                            float& cover, int qpt = 32) {
     // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
     // margin: 2e-3 cells absolute plus 2.4e-7 relative to the coordinate (one float ulp), on top of the
     // 1e-6 relative slack of the radius.
@@ -395,6 +434,10 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
     L.sxy = list;
     L.szw = list + LEAN_LIST_CAP;
     L.n = 0;
+    // qpt < 32 (8): lanes l, l + 8, l + 16, l + 24 carry the same query, seed and state; they differ in the list entries
+    // they evaluate, and are merged after every walk
+    L.nrep = 32 / qpt;
+    L.rep = (int)(threadIdx.x & 31) / qpt;
 #if R3D_LEAN_TMA
     L.stage = list + 2 * LEAN_LIST_CAP;
     L.stage_addr = smem_u32(L.stage);
@@ -463,13 +506,13 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
         } else {
             // far outliers / queries far outside the cloud / badly misaligned pairs: the served lanes are searched one
             // at a time, the whole warp working for each (far_query_search)
-            unsigned todo = __ballot_sync(FULL, part);
+            unsigned todo = __ballot_sync(FULL, part && (int)(threadIdx.x & 31) < qpt);      // one replica of each query
             while (todo) {
                 const int owner = __ffs(todo) - 1;
                 todo &= todo - 1u;
                 bool all_scanned = false;
                 const Best found = far_query_search(owner, seed, v, g, qx, qy, qz, ruse, all_scanned);
-                if ((int)(threadIdx.x & 31) == owner) {
+                if ((int)(threadIdx.x & 31) % qpt == owner) {
                     if (found.d2 < other.d2 || (found.d2 == other.d2 && found.idx < other.idx)) other = found;
                     const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                     fin = all_scanned || (rn <= ruse) || !(ruse < 1e37f);

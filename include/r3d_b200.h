@@ -277,6 +277,7 @@ int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* queries, in
  * evaluations per lane, searches skipped (lanes), segment lookup rounds, segments looked up, non-empty
  * segments, skipped lanes whose seed was beaten by an evaluated point (must be 0).  Synchronous. */
 int r3d_nn_stats_read(uint64_t* out8_host, int reset);
+int r3d_nn_stats_read_ext(uint64_t* out16_host, int reset);   /* + 8 far-path / task-duration counters (csrc/lean_search.cuh) */
 
 #ifdef __cplusplus
 }

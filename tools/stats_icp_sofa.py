@@ -35,8 +35,10 @@ L.r3d_nn_timing_enable(0)
 print("factor %.2f: icp %.2f ms for %d iterations; nn kernel %.2f ms over %d launches (%.1f us each); mean dist %.3f" % (
     factor, dt * 1e3, iters, ms.value, n.value, 1e3 * ms.value / max(n.value, 1), d.mean()))
 if has_stats:
-    st = (ctypes.c_uint64 * 8)()
-    L.r3d_nn_stats_read(st, 1)
+    st = (ctypes.c_uint64 * 16)()
+    L.r3d_nn_stats_read_ext(st, 1)
     tasks = max(int(st[0]), 1)
     print("per task: rounds %.2f, candidates/lane %.1f, lanes skipped %.2f, lookup rounds %.2f, segments %.1f, non-empty %.1f" % (
         st[1] / tasks, st[2] / tasks, st[3] / tasks, st[4] / tasks, st[5] / tasks, st[6] / tasks))
+    print("far searches/task %.3f, sweep steps/far %.1f, scan steps/far %.1f, block-granular walks/task %.3f | task cycles: mean %.0f, max %d" % (
+        st[8] / tasks, st[9] / max(int(st[8]), 1), st[10] / max(int(st[8]), 1), st[11] / tasks, st[12] / tasks, st[13]))
