@@ -708,7 +708,7 @@ sel_hist_kernel(IcpWorkspace w, int pass) {
     const PairState* st = w.state + pair;
     const SelState sel = w.sel[pair];
     const int n = st->n_src;
-    if (st->done || st->cutoff >= n || st->cutoff <= 0) return;      // nothing to select (see sel_pick_kernel)
+    if (st->done || st->cutoff >= n || st->cutoff <= 0 || n <= NN_SMALL_PAIR) return;      // nothing to select (see sel_pick_step) / small pair
     const int base = blockIdx.x * SEL_TILE;
     if (base >= n) return;
     __shared__ uint32_t hist[SEL_BINS];
@@ -745,13 +745,11 @@ sel_hist_kernel(IcpWorkspace w, int pass) {
     }
 }
 
-// one CTA per pair: find the bin that holds rank k, descend into it; after the last pass publish the
-// threshold and, when exact ties straddle the cutoff, the largest source index kept among them
-__global__ void __launch_bounds__(1024)
-sel_pick_kernel(IcpWorkspace w, int pass) {
-    const int pair = blockIdx.x;
+// One step of the descent, by a CTA of 1024 threads: find the bin of `gh` (SEL_BINS counters, global or shared; zeroed
+// here for the next selection) that holds rank k and descend into it; after the last pass publish the threshold and,
+// when exact ties straddle the cutoff, the largest source index kept among them.
+__device__ __forceinline__ void sel_pick_step(IcpWorkspace& w, int pair, int pass, uint32_t* gh) {
     PairState* st = w.state + pair;
-    if (st->done) return;
     SelState* sel = w.sel + pair;
     const int n = st->n_src, cutoff = st->cutoff;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -769,10 +767,9 @@ sel_pick_kernel(IcpWorkspace w, int pass) {
         __syncthreads();
     }
     if (trivial) return;
-    uint32_t* gh = w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS;
     // 2 bins per thread, exclusive scan over the CTA
     const uint32_t c0 = gh[2 * threadIdx.x], c1 = gh[2 * threadIdx.x + 1];
-    gh[2 * threadIdx.x] = 0;          // ready for the next iteration's selection
+    gh[2 * threadIdx.x] = 0;          // ready for the next pass / the next iteration's selection
     gh[2 * threadIdx.x + 1] = 0;
     const uint32_t tot = c0 + c1;
     uint32_t x = tot;
@@ -805,8 +802,8 @@ sel_pick_kernel(IcpWorkspace w, int pass) {
         sel->k = k - before - (first ? 0u : c0);
         sel->neq = first ? c0 : c1;
     }
-    if (pass != SEL_PASSES - 1) return;
     __syncthreads();
+    if (pass != SEL_PASSES - 1) return;
     const unsigned long long tau_bits = sel->prefix;
     const uint32_t quota = sel->k + 1;     // how many elements equal to tau belong to the kept set
     const uint32_t neq = sel->neq;
@@ -836,6 +833,48 @@ sel_pick_kernel(IcpWorkspace w, int pass) {
     if (threadIdx.x == 0) {
         st->tau = __longlong_as_double((long long)tau_bits);
         st->idx_cut = s_idx_cut;
+    }
+}
+
+// Pairs of at most NN_SMALL_PAIR source points are selected by sel_small_kernel below, the others by the
+// multi-CTA histogram passes.
+__device__ __forceinline__ bool sel_is_small(int n_src) { return n_src <= NN_SMALL_PAIR; }
+
+__global__ void __launch_bounds__(1024)
+sel_pick_kernel(IcpWorkspace w, int pass) {
+    const int pair = blockIdx.x;
+    const PairState* st = w.state + pair;
+    if (st->done || sel_is_small(st->n_src)) return;
+    sel_pick_step(w, pair, pass, w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS);
+}
+
+// The whole selection of a small pair in one launch: one CTA, the six histogram + pick steps back to back on a
+// shared-memory histogram (the keys, at most 256 KB, stay in L1/L2).  For the reference's own cloud sizes the twelve
+// launches of the general path cost more than the search itself.
+__global__ void __launch_bounds__(1024)
+sel_small_kernel(IcpWorkspace w) {
+    const int pair = blockIdx.x;
+    const PairState* st = w.state + pair;
+    const int n = st->n_src;
+    if (st->done || !sel_is_small(n)) return;
+    __shared__ uint32_t hist[SEL_BINS];
+    for (int k = threadIdx.x; k < SEL_BINS; k += 1024) hist[k] = 0;
+    const bool trivial = st->cutoff >= n || st->cutoff <= 0;
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(w.d2 + (size_t)pair * w.max_src);
+    for (int pass = 0; pass < SEL_PASSES; pass++) {
+        __syncthreads();
+        if (!trivial) {
+            const unsigned long long prefix = pass == 0 ? 0ull : w.sel[pair].prefix;
+            const int shift = sel_shift(pass);
+            const uint32_t mask = (1u << sel_bits(pass)) - 1u;
+            for (int i = threadIdx.x; i < n; i += 1024) {
+                const unsigned long long key = keys[i];
+                if (pass == 0 || (key >> (shift + sel_bits(pass))) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & mask], 1u);
+            }
+        }
+        __syncthreads();
+        sel_pick_step(w, pair, pass, hist);
+        if (trivial) return;      // pass 0 has published "keep everything / nothing"
     }
 }
 
@@ -1147,9 +1186,12 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
             if (rc != R3D_OK) return rc;
         }
         if (!fused) {
-            for (int pass = 0; pass < SEL_PASSES; pass++) {
-                R3D_LAUNCH(sel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
-                R3D_LAUNCH(sel_pick_kernel, P, 1024, 0, st, w, pass);
+            R3D_LAUNCH(sel_small_kernel, P, 1024, 0, st, w);
+            if (w.max_src > NN_SMALL_PAIR) {
+                for (int pass = 0; pass < SEL_PASSES; pass++) {
+                    R3D_LAUNCH(sel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
+                    R3D_LAUNCH(sel_pick_kernel, P, 1024, 0, st, w, pass);
+                }
             }
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
         }

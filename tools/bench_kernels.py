@@ -243,18 +243,22 @@ out["K7_voxel_downsample"] = {"what": "2 M points, voxel 2 -> %d voxels (bbox, c
                               "frac_of_hbm": algo / ms / 1e6 / HBM}
 
 # ---- configs[3]: one 2 M x 2 M pair, 30 iterations (single GPU; SURVEY 8e: replicas only) --------------------------------
-icp_mod = importlib.import_module("2dto3dreconstruction_b200.utils.icp")
-from oracle import ref_port as O  # noqa: E402  (input generation only)
 if True:
-    fa2, _ = O.synth_depth_pair(0, h=1226, w=1632, seed_base=7)          # SURVEY 8d C4, as tests/test_gpu_full_size.py
-    A2 = O.depth_to_voxel_ld(fa2)
+    # SURVEY 8d C4 built on the device (same surface model as tests/test_gpu_full_size.py, torch RNG): a 1632x1226 depth
+    # frame back-projected with the _ld intrinsics, dst = rigid motion (2 degrees about z, t = (15,-8,5)) + N(0, 0.5)
+    hh, ww = 1226, 1632
+    uu = torch.arange(ww, dtype=torch.float64, device=dev)[None, :].expand(hh, ww)
+    vv = torch.arange(hh, dtype=torch.float64, device=dev)[:, None].expand(hh, ww)
+    dd = torch.round(2000 + 600 * torch.sin(uu / 97) + 400 * torch.cos(vv / 61) + 2 * torch.randn((hh, ww), dtype=torch.float64, device=dev, generator=g))
+    keep = torch.rand((hh, ww), device=dev, generator=g) >= 0.1
+    dd, uu, vv = dd[keep], uu[keep], vv[keep]
+    A2 = torch.stack(((uu - 319.5) * dd / 525.0, (vv - 239.5) * dd / 525.0, dd), dim=1).contiguous()
     ang = np.deg2rad(2.0)
-    Tt = np.eye(4)
-    Tt[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
-    Tt[:3, 3] = [15.0, -8.0, 5.0]
-    B2 = O.get_transformed_points(A2, Tt) + np.random.default_rng(7).normal(0.0, 0.5, size=A2.shape)
-    a4 = ops.pack_xyzw(C.to_device(np.ascontiguousarray(A2)))
-    b4 = ops.pack_xyzw(C.to_device(np.ascontiguousarray(B2)))
+    Rz = torch.tensor([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]], dtype=torch.float64, device=dev)
+    B2 = (A2 @ Rz.T + torch.tensor([15.0, -8.0, 5.0], dtype=torch.float64, device=dev)
+          + 0.5 * torch.randn(A2.shape, dtype=torch.float64, device=dev, generator=g)).contiguous()
+    a4 = ops.pack_xyzw(A2)
+    b4 = ops.pack_xyzw(B2)
     oa = torch.tensor([0, len(A2)], dtype=torch.int32, device=dev)
     ob = torch.tensor([0, len(B2)], dtype=torch.int32, device=dev)
     bws = L.r3d_icp_workspace_bytes(1, len(A2), len(B2))
