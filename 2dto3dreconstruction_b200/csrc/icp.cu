@@ -31,7 +31,13 @@ constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A funct
 // evaluate a quarter of the candidates: four times the warps, a quarter of the per-task serial work.  Also a
 // function of the pair alone.
 constexpr int NN_SMALL_PAIR = 1 << 15;
-__host__ __device__ __forceinline__ int queries_per_task(int n_src) { return n_src <= NN_SMALL_PAIR ? 8 : 32; }
+#ifndef R3D_NN_MID_PAIR
+#define R3D_NN_MID_PAIR 0
+#endif
+constexpr int NN_MID_PAIR = R3D_NN_MID_PAIR;      // up to this many points: 16 queries per task on two lanes each (0 = off)
+__host__ __device__ __forceinline__ int queries_per_task(int n_src) {
+    return n_src <= NN_SMALL_PAIR ? 8 : (n_src <= NN_MID_PAIR ? 16 : 32);
+}
 __host__ __device__ __forceinline__ int vwarps_for(int n_src) { return n_src > NN_VWARPS_BIG_FROM ? NN_VWARPS_BIG : NN_VWARPS; }
 
 struct PairState {

@@ -107,7 +107,7 @@ struct WarpList {
     double2* sxy;      // [LEAN_LIST_CAP] (x, y)
     double2* szw;      // [LEAN_LIST_CAP] (z, tag)
     int n;             // warp-uniform
-    int nrep, rep;     // small pairs: every query sits on nrep = 4 lanes (replica rep = lane / 8), else nrep = 1, rep = 0
+    int nrep, rep;     // small pairs: every query sits on nrep = 4 (or 2) lanes, replica rep = lane / (32 / nrep); else nrep = 1, rep = 0
     double lo[3], hi[3];      // filter box (world coordinates)
 #if R3D_LEAN_TMA
     const double2* stage;     // two staging buffers of 32 raw 32-byte records each, filled by cp.async.bulk
@@ -124,10 +124,11 @@ __device__ __forceinline__ void list_flush(WarpList& L, Best& best, int seed_pos
     const int n = L.n;
     R3D_STAT(2, (n + 3) & ~3);
     if (L.nrep > 1) {
-        // replica r of a query takes entries r, r + 4, ...: a quarter of the scan each (lean_scan_box merges them)
+        // replica r of a query takes entries r, r + nrep, ...: a quarter (half) of the scan each (lean_scan_box merges them)
+        const int nrep = L.nrep;
 #pragma unroll 1
-        for (int u = L.rep; u < n; u += 8) {
-            const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + 4], b1 = L.szw[u + 4];
+        for (int u = L.rep; u < n; u += 2 * nrep) {
+            const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + nrep], b1 = L.szw[u + nrep];
             eval_staged(best, seed_pos, a0, b0, qx, qy, qz);
             eval_staged(best, seed_pos, a1, b1, qx, qy, qz);
         }
@@ -300,8 +301,7 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
     if (L.nrep > 1) {
         // the four replicas of a query have each seen a quarter of the candidates: give all of them the minimum, so
         // that they keep taking the same decisions
-#pragma unroll
-        for (int o = 8; o <= 16; o <<= 1) {
+        for (int o = 32 / L.nrep; o < 32; o <<= 1) {
             const double od2 = __shfl_xor_sync(FULL, best.d2, o);
             const int oidx = __shfl_xor_sync(FULL, best.idx, o), opos = __shfl_xor_sync(FULL, best.pos, o);
             if (od2 < best.d2 || (od2 == best.d2 && oidx < best.idx)) { best.d2 = od2; best.idx = oidx; best.pos = opos; }
@@ -434,7 +434,7 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
     L.sxy = list;
     L.szw = list + LEAN_LIST_CAP;
     L.n = 0;
-    // qpt < 32 (8): lanes l, l + 8, l + 16, l + 24 carry the same query, seed and state; they differ in the list entries
+    // qpt < 32 (8 or 16): lanes l, l + qpt, ... carry the same query, seed and state; they differ in the list entries
     // they evaluate, and are merged after every walk
     L.nrep = 32 / qpt;
     L.rep = (int)(threadIdx.x & 31) / qpt;

@@ -272,3 +272,35 @@ def test_search_skipping_is_exact_far_from_the_origin(offset):
     assert np.array_equal(on["T"].cpu().numpy(), off["T"].cpu().numpy())
     assert np.array_equal(on["idx"].cpu().numpy(), off["idx"].cpu().numpy())
     assert np.array_equal(on["dist"].cpu().numpy(), off["dist"].cpu().numpy())
+
+
+@pytest.mark.parametrize("n_side,partial", [(27, 0.5), (27, 0.9), (37, 0.5), (37, 0.31)])      # 19 683 points: one-launch select; 50 653: general path
+def test_partial_set_with_exact_ties_at_the_cutoff(n_side, partial):
+    """utils/icp.py:109-110 keeps exactly int(N * p) correspondences.  On a lattice shifted by half a cell every
+    distance is the same double, so the k-th smallest distance is tied N times and the selection has to cut inside
+    the ties (the reference's argpartition order among equal keys is unspecified; here the lowest positions are
+    kept): the count must still be exact, for the single-launch select of small pairs and the multi-pass one."""
+    ops = sub("ops")
+    C = sub("_capi")
+    g = np.arange(n_side, dtype=np.float64) * 4.0
+    A = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3)
+    B = A + np.array([2.0, 0.0, 0.0])
+    rng = np.random.default_rng(n_side)
+    A = A[rng.permutation(len(A))]
+    far = rng.random(len(A)) < 0.2                   # a fifth of the queries are strictly farther: 2 < sqrt(5)
+    A[far, 1] += 1.0
+    n = len(A)
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    r = ops.icp_batch(s, ops._offsets([n]), d, ops._offsets([len(B)]), 1, n, len(B), max_iterations=1, tolerance=0.0,
+                      partial_set_size=partial, want_last=True)
+    keep = r["keep"].cpu().numpy().astype(bool)
+    dist = r["dist"].cpu().numpy()
+    cutoff = int(n * partial)
+    assert keep.sum() == cutoff
+    n_near = int((~far).sum())
+    assert np.all(dist[~far] == 2.0) and np.all(dist[far] == np.sqrt(5.0))
+    if cutoff <= n_near:
+        assert not keep[far].any()                   # the cut falls inside the tied distances
+    else:
+        assert keep[~far].all() and keep[far].sum() == cutoff - n_near

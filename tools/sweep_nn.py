@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ctypes  # noqa: E402
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import bench  # noqa: E402
@@ -29,6 +30,15 @@ pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
 C = importlib.import_module("2dto3dreconstruction_b200._capi")
 L = C.lib()
 a, b = bench.synth_batch_torch(pairs, 0, torch.device("cuda", 0))
+if os.environ.get("SWEEP_CROP"):      # "w,h": keep a centred window of the frames only (smaller clouds, same point spacing)
+    cw, ch = (int(x) for x in os.environ["SWEEP_CROP"].split(","))
+    def crop(x):      # through NumPy: torch has no uint16 arithmetic on the device
+        h = x.cpu().numpy().copy()
+        m = np.zeros(h.shape[1:], dtype=bool)
+        m[(480 - ch) // 2:(480 + ch) // 2, (640 - cw) // 2:(640 + cw) // 2] = True
+        h[:, ~m] = 0
+        return torch.from_numpy(h).cuda()
+    a, b = crop(a), crop(b)
 kw = dict(max_iterations=iters, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)
 ref = None
 for cfg in configs.split(","):
