@@ -568,6 +568,11 @@ struct LeanTuning {
 // (Packing the lanes that still need a search into full warps through a per-warp queue was tried and
 // measured slower -- 339 vs 302 us per launch: the packed warps span several tasks, so their union boxes
 // grow as fast as the number of searches shrinks; profiles/r01_nn_sweeps.md, sweep_8.)
+#ifndef R3D_NN_PREFETCH
+#define R3D_NN_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool SEEDED, bool FUSED>
 __global__ void __launch_bounds__(NN_THREADS, R3D_LEAN_MIN_CTAS)
 nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
@@ -624,6 +629,22 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             const int i = task * qpt + (lane & (qpt - 1));      // qpt = 8: four lanes per query (lean_search)
             const bool active = i < s_n;
             const bool primary = lane < qpt;                    // the replica that writes the results
+#if R3D_NN_PREFETCH
+            // The virtual warp's next task is 2048 tasks away: nothing of it is in cache.  Once most lanes skip their
+            // search a task is a chain of dependent loads (query, previous neighbour's position, that point), so ask
+            // for the next task's lines now and for its neighbour points at the end of this task.
+            int pos_next = -1;
+            {
+                const int in = (task + nvw) * qpt + (lane & (qpt - 1));
+                if (task + nvw < n_tasks && in < s_n) {
+                    prefetch_l2(src + in);
+                    if (SEEDED) {
+                        pos_next = nn_pos[in];
+                        prefetch_l2(budget + in);
+                    }
+                }
+            }
+#endif
             double qx = 0.0, qy = 0.0, qz = 0.0;
             Best seed, other;
             seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
@@ -680,6 +701,9 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 }
                 budget[i] = nb;
             }
+#if R3D_NN_PREFETCH
+            if (SEEDED && pos_next >= 0) prefetch_l2(v.pts + pos_next);
+#endif
             if (FUSED) {
                 double m[16];
 #pragma unroll
