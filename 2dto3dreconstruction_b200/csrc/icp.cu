@@ -27,16 +27,20 @@ constexpr int NN_VWARPS_BIG = 8192;  // ... and for a pair of more than NN_VWARP
 constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A function of the pair alone, so batching stays irrelevant.
 // Queries per task of the lean kernel: a warp normally takes 32 consecutive queries; a SMALL pair (the reference's
 // own sizes: 13k-26k points after its sub-sampling) would then give a few hundred warps, one per SM sub-partition,
-// each running its whole search serially.  Such pairs use 8 queries per task, every query on four lanes that each
-// evaluate a quarter of the candidates: four times the warps, a quarter of the per-task serial work.  Also a
-// function of the pair alone.
+// each running its whole search serially.  Such pairs use 4 queries per task, every query on eight lanes that each
+// evaluate an eighth of the candidates: eight times the warps, an eighth of the per-task serial scan.  Also a
+// function of the pair alone.  (8 / 4 / 2 queries per task on the sofa pair: 149 / 140 / 164 us per launch at
+// partial_set_size 1.0, 203 / 163 / 149 us at 0.7.)
 constexpr int NN_SMALL_PAIR = 1 << 15;
 #ifndef R3D_NN_MID_PAIR
 #define R3D_NN_MID_PAIR 0
 #endif
 constexpr int NN_MID_PAIR = R3D_NN_MID_PAIR;      // up to this many points: 16 queries per task on two lanes each (0 = off)
+#ifndef R3D_NN_SMALL_QPT
+#define R3D_NN_SMALL_QPT 4
+#endif
 __host__ __device__ __forceinline__ int queries_per_task(int n_src) {
-    return n_src <= NN_SMALL_PAIR ? 8 : (n_src <= NN_MID_PAIR ? 16 : 32);
+    return n_src <= NN_SMALL_PAIR ? R3D_NN_SMALL_QPT : (n_src <= NN_MID_PAIR ? 16 : 32);
 }
 __host__ __device__ __forceinline__ int vwarps_for(int n_src) { return n_src > NN_VWARPS_BIG_FROM ? NN_VWARPS_BIG : NN_VWARPS; }
 
@@ -58,7 +62,8 @@ struct SelState {          // radix-select progress of one pair
     unsigned long long prefix;
     uint32_t k;            // rank still to find inside the prefix
     uint32_t neq;          // keys in the chosen bin
-    int pad[2];
+    int finished;          // the descent ended early: every key of the chosen bin belongs to the kept set
+    int pad;
 };
 
 struct IcpWorkspace {
@@ -626,7 +631,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
         for (int task = vw; task < n_tasks; task += nvw) {
-            const int i = task * qpt + (lane & (qpt - 1));      // qpt = 8: four lanes per query (lean_search)
+            const int i = task * qpt + (lane & (qpt - 1));      // qpt < 32: 32 / qpt lanes per query (lean_search)
             const bool active = i < s_n;
             const bool primary = lane < qpt;                    // the replica that writes the results
 #if R3D_NN_PREFETCH
@@ -739,6 +744,7 @@ sel_hist_kernel(IcpWorkspace w, int pass) {
     const SelState sel = w.sel[pair];
     const int n = st->n_src;
     if (st->done || st->cutoff >= n || st->cutoff <= 0 || n <= NN_SMALL_PAIR) return;      // nothing to select (see sel_pick_step) / small pair
+    if (pass > 0 && sel.finished) return;
     const int base = blockIdx.x * SEL_TILE;
     if (base >= n) return;
     __shared__ uint32_t hist[SEL_BINS];
@@ -792,11 +798,13 @@ __device__ __forceinline__ void sel_pick_step(IcpWorkspace& w, int pair, int pas
         if (threadIdx.x == 0) {
             sel->prefix = 0ull;
             sel->k = (uint32_t)max(cutoff - 1, 0);
+            sel->finished = 0;
             if (trivial) { st->tau = (cutoff >= n) ? CUDART_INF : -1.0; st->idx_cut = 0x7fffffff; }
         }
         __syncthreads();
     }
     if (trivial) return;
+    if (pass > 0 && sel->finished) return;      // (uniform: written before the last barrier of an earlier step)
     // 2 bins per thread, exclusive scan over the CTA
     const uint32_t c0 = gh[2 * threadIdx.x], c1 = gh[2 * threadIdx.x + 1];
     gh[2 * threadIdx.x] = 0;          // ready for the next pass / the next iteration's selection
@@ -829,11 +837,22 @@ __device__ __forceinline__ void sel_pick_step(IcpWorkspace& w, int pair, int pas
         const bool first = k < before + c0;
         const uint32_t bin = 2 * threadIdx.x + (first ? 0 : 1);
         sel->prefix = (prefix << sel_bits(pass)) | (unsigned long long)bin;
-        sel->k = k - before - (first ? 0u : c0);
-        sel->neq = first ? c0 : c1;
+        const uint32_t kk = k - before - (first ? 0u : c0), neq = first ? c0 : c1;
+        sel->k = kk;
+        sel->neq = neq;
+        if (pass != SEL_PASSES - 1 && kk + 1 == neq) {
+            // The rank falls on the LAST key of its bin: every key of the bin is kept, so the low bits of the threshold
+            // do not matter -- keep everything up to the largest key the bin can hold and skip the remaining passes
+            // (with 2 M distinct distances the bin of the third pass usually holds one key).
+            const unsigned long long pre = (prefix << sel_bits(pass)) | (unsigned long long)bin;
+            const int sh = sel_shift(pass);
+            st->tau = __longlong_as_double((long long)((pre << sh) | ((1ull << sh) - 1ull)));
+            st->idx_cut = 0x7fffffff;
+            sel->finished = 1;
+        }
     }
     __syncthreads();
-    if (pass != SEL_PASSES - 1) return;
+    if (pass != SEL_PASSES - 1 || sel->finished) return;
     const unsigned long long tau_bits = sel->prefix;
     const uint32_t quota = sel->k + 1;     // how many elements equal to tau belong to the kept set
     const uint32_t neq = sel->neq;
@@ -904,7 +923,7 @@ sel_small_kernel(IcpWorkspace w) {
         }
         __syncthreads();
         sel_pick_step(w, pair, pass, hist);
-        if (trivial) return;      // pass 0 has published "keep everything / nothing"
+        if (trivial || w.sel[pair].finished) return;      // pass 0 has published "keep everything / nothing" / early end
     }
 }
 

@@ -126,11 +126,16 @@ __device__ __forceinline__ void list_flush(WarpList& L, Best& best, int seed_pos
     if (L.nrep > 1) {
         // replica r of a query takes entries r, r + nrep, ...: a quarter (half) of the scan each (lean_scan_box merges them)
         const int nrep = L.nrep;
+        if (nrep <= 4) {
 #pragma unroll 1
-        for (int u = L.rep; u < n; u += 2 * nrep) {
-            const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + nrep], b1 = L.szw[u + nrep];
-            eval_staged(best, seed_pos, a0, b0, qx, qy, qz);
-            eval_staged(best, seed_pos, a1, b1, qx, qy, qz);
+            for (int u = L.rep; u < n; u += 2 * nrep) {      // reads up to slot n - 1 + nrep < LEAN_LIST_CAP: a real point
+                const double2 a0 = L.sxy[u], b0 = L.szw[u], a1 = L.sxy[u + nrep], b1 = L.szw[u + nrep];
+                eval_staged(best, seed_pos, a0, b0, qx, qy, qz);
+                eval_staged(best, seed_pos, a1, b1, qx, qy, qz);
+            }
+        } else {
+#pragma unroll 1
+            for (int u = L.rep; u < n; u += nrep) eval_staged(best, seed_pos, L.sxy[u], L.szw[u], qx, qy, qz);
         }
         __syncwarp();
         L.n = 0;
