@@ -149,3 +149,39 @@ def test_register_imgs_end_to_end_on_the_sofa_frames():
     np.random.choice(clouds[1].shape[0], int(clouds[1].shape[0] * 0.05), replace=False)
     np.random.choice(clouds[0].shape[0], int(clouds[0].shape[0] * 0.05), replace=False)
     assert after == np.random.randint(1 << 30)
+
+
+def test_kitchen_pair_against_the_reference_run():
+    """BASELINE.json configs[1] (`reconstruct_rgbd.py --mode rigid3d`), one pair: the CUDA drop-ins against the recorded
+    run of the reference's rigid3d_proc loop body (reconstruct.py:264-278) on examples/kitchen_rgbd frames 1-2:
+    q8.mathching_skimage (K5 + ratio test) -> q9.ransac_loop (K4A) -> r3d.rigid_transform_3D (K3).  Match lists and
+    the RANSAC inlier set are identical, the homography and the rigid transform agree to rounding."""
+    import contextlib
+    import io
+    import warnings
+    from conftest import load_golden
+    q8 = sub("utils.homography_utils.q8")
+    q9 = sub("utils.homography_utils.q9")
+    r3d = sub("utils.r3d")
+    g = load_golden("kitchen_pair")
+
+    class KP:
+        def __init__(self, p):
+            self.pt = (float(p[0]), float(p[1]))
+
+    kp1, kp2 = [KP(p) for p in g["kp1"]], [KP(p) for p in g["kp2"]]
+    img = np.zeros(tuple(g["img_shape"]), np.uint8)
+    bf = q8.mathching_skimage(img, kp1, g["des1"].astype(np.float32), img, kp2, g["des2"].astype(np.float32), False)
+    assert np.array_equal(bf, g["bf"]), "ratio-test matches differ from the reference run's"
+    np.random.seed(0)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        H, fm = q9.ransac_loop(img, img, kp1, kp2, bf)
+        assert np.array_equal(fm, g["matches"]), "RANSAC inlier set differs from the reference's"
+        np.testing.assert_allclose(H, g["H"], rtol=1e-9, atol=1e-12)
+        m1 = [g["kps3d_1"][m[0]] for m in fm]                      # reconstruct.py:271-278
+        m2 = [g["kps3d_2"][m[1]] for m in fm]
+        R, t = r3d.rigid_transform_3D(np.array(m1).T, np.array(m2).T)
+    assert R.shape == (3, 3) and t.shape == (3, 1)
+    np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(t, g["t"], rtol=0, atol=1e-8)

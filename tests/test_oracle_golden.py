@@ -211,3 +211,22 @@ def test_skimage_match_restatement_hand_example():
     # ratios: 1/8.60 = 0.116, 1/8.60 = 0.116, 5.83/10.05 = 0.580
     assert np.array_equal(O.match_descriptors_skimage(d1, d2, max_ratio=0.5, cross_check=True), [[0, 0], [1, 1]])
     assert np.array_equal(O.match_descriptors_skimage(d1, d2, max_ratio=0.8, cross_check=True), [[0, 0], [1, 1], [2, 2]])
+
+
+def test_kitchen_pair_reference_run():
+    """BASELINE.json configs[1] (`--mode rigid3d`), one pair: the loop body of the reference's rigid3d_proc
+    (reconstruct.py:264-278) run by tests/golden/make_golden_kitchen.py on examples/kitchen_rgbd frames 1-2.  The oracle
+    must reproduce the matching stage, the seeded RANSAC stage and the rigid fit on the matched 3-D keypoints."""
+    import warnings
+    g = load_golden("kitchen_pair")
+    bf = O.match_descriptors_skimage(g["des1"].astype(np.float32), g["des2"].astype(np.float32), max_ratio=0.8, cross_check=True)
+    assert np.array_equal(bf, g["bf"])
+    np.random.seed(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        H, fm, counts = O.ransac_loop_pts(tuple(g["img_shape"]), g["kp1"], g["kp2"], g["bf"])
+    assert np.array_equal(fm, g["matches"])
+    np.testing.assert_allclose(H, g["H"], rtol=1e-9, atol=1e-12)
+    R, t = O.rigid_transform_3D(g["kps3d_1"][fm[:, 0]].T, g["kps3d_2"][fm[:, 1]].T)
+    np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(t, g["t"], rtol=0, atol=1e-9)
