@@ -26,6 +26,9 @@ class IcpParams(ctypes.Structure):
                 ("partial_set_size", c_double), ("cell_size", c_double)]
 
 
+#: r3d_exchange_fn (include/r3d_b200.h): int (*)(void* ctx, void* device_buf, size_t n_doubles, void* stream)
+EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_size_t, c_void_p)
+
 #: every symbol include/r3d_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "r3d_version": (c_int, []),
@@ -49,6 +52,9 @@ SIGNATURES = {
     "r3d_icp_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                               ctypes.POINTER(IcpParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_size_t, c_void_p]),
+    "r3d_icp_batch_sharded": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                      ctypes.POINTER(IcpParams), c_int, c_int, EXCHANGE_FN, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_size_t, c_void_p]),
     "r3d_ransac2d_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "r3d_ransac2d_score": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -68,6 +68,7 @@ struct SelState {          // radix-select progress of one pair
 
 struct IcpWorkspace {
     GridWorkspace grid;
+    int shard_rank, shard_world;      // query sharding of r3d_icp_batch_sharded: this process runs virtual warps rank, rank + world, ...
     int n_pairs, max_src, src_tiles, src_rows;
     PairState* state;      // [pair]
     SortDesc* src_desc;    // [pair]
@@ -98,6 +99,8 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     grid_workspace_layout(w.grid, a, n_pairs, max_dst);
     w.n_pairs = n_pairs;
     w.max_src = max_src;
+    w.shard_rank = 0;
+    w.shard_world = 1;
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
     w.src_rows = w.src_tiles * (NN_THREADS / 32);
@@ -627,7 +630,7 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     while (true) {
         int vw = 0;
         if (lane == 0) vw = atomicAdd(vw_counter, 1);
-        vw = __shfl_sync(0xffffffffu, vw, 0);
+        vw = __shfl_sync(0xffffffffu, vw, 0) * w.shard_world + w.shard_rank;      // (1, 0 unless the queries are sharded over GPUs)
         if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
         for (int task = vw; task < n_tasks; task += nvw) {
@@ -1212,10 +1215,27 @@ static int sort_source(IcpWorkspace& w, const Point4* src, const int32_t* src_of
     return R3D_OK;
 }
 
+// Query sharding over GPUs (r3d_icp_batch_sharded): every process holds both clouds and runs the same launches, but its
+// nn kernel only takes the virtual warps vw = rank (mod world).  A virtual warp's row of moment sums is written by
+// exactly one process and is zero everywhere else, so the SUM exchange of the row table reproduces the single-GPU table
+// bit for bit (x + 0 + ... + 0 = x whatever the reduction order) and solve_kernel, which adds the rows in a fixed
+// order on every process, produces the single-GPU transform on all of them.
+struct IcpShard {
+    int rank, world;
+    r3d_exchange_fn exchange;
+    void* ctx;
+};
+
 int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Point4* dst, const int32_t* dst_off,
             const double* init_pose, const r3d_icp_params& prm, double* T_out, int32_t* iters_out, double* mean_err_out,
-            int32_t* last_idx, double* last_dist, uint8_t* last_keep, cudaStream_t st) {
+            int32_t* last_idx, double* last_dist, uint8_t* last_keep, cudaStream_t st, const IcpShard* shard = nullptr) {
     const int P = w.n_pairs;
+    const bool sharded = shard != nullptr && shard->world > 1;
+    if (sharded) {
+        w.shard_rank = shard->rank;
+        w.shard_world = shard->world;
+    }
+    const size_t shard_doubles = (size_t)vwarps_for(w.max_src) * 16;      // one pair (checked by the caller): rows [0, nvw)
     int rc = grid_build(w.grid, dst, dst_off, prm.cell_size, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(state_init_kernel, (P + 127) / 128, 128, 0, st, w, src_off, init_pose, prm.partial_set_size);
@@ -1229,10 +1249,15 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
     if (!fused) R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * SEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
     for (int it = 0; it < prm.max_iterations; it++) {
+        if (sharded) R3D_CUDA(cudaMemsetAsync(w.partial, 0, shard_doubles * sizeof(double), st));
         {
             NnTimer timer(st);
             rc = launch_nn(w, nngrid, it > 0, fused, fused ? want_d2 : 1, st);
             if (rc != R3D_OK) return rc;
+        }
+        if (sharded) {
+            // the caller's collective (NCCL all-reduce through torch.distributed in the shipped binding), ordered on `st`
+            if (shard->exchange(shard->ctx, w.partial, shard_doubles, (void*)st) != 0) return R3D_ERR_INVALID;
         }
         if (!fused) {
             R3D_LAUNCH(sel_small_kernel, P, 1024, 0, st, w);
@@ -1311,6 +1336,25 @@ extern "C" int r3d_icp_batch(const double* src, const int32_t* src_off, const do
     if (rc != R3D_OK) return rc;
     return icp_run(w, (const Point4*)src, src_off, (const Point4*)dst, dst_off, init_pose, *params, T_out, iters_out,
                    mean_err_out, last_idx, last_dist, last_keep, (cudaStream_t)stream);
+}
+
+extern "C" int r3d_icp_batch_sharded(const double* src, const int32_t* src_off, const double* dst, const int32_t* dst_off,
+                                     int n_pairs, int max_src, int max_dst, const double* init_pose, const r3d_icp_params* params,
+                                     int rank, int world, r3d_exchange_fn exchange, void* exchange_ctx, double* T_out,
+                                     int32_t* iters_out, double* mean_err_out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (!src || !src_off || !dst || !dst_off || !params || !T_out || max_src <= 0 || max_dst <= 0) return R3D_ERR_INVALID;
+    if (n_pairs != 1) return R3D_ERR_INVALID;                       // one (large) pair; batches shard by pair instead
+    if (world < 1 || rank < 0 || rank >= world || world > NN_VWARPS || (world > 1 && !exchange)) return R3D_ERR_INVALID;
+    if (params->max_iterations < 0 || params->partial_set_size != 1.0) return R3D_ERR_INVALID;      // see include/r3d_b200.h
+    if ((((uintptr_t)src) & 31) || (((uintptr_t)dst) & 31)) return R3D_ERR_INVALID;
+    if (g_nn_impl.load() != 1) return R3D_ERR_INVALID;
+    IcpWorkspace w;
+    int rc = icp_workspace_bind(w, workspace, workspace_bytes, n_pairs, max_src, max_dst);
+    if (rc != R3D_OK) return rc;
+    IcpShard shard{rank, world, exchange, exchange_ctx};
+    return icp_run(w, (const Point4*)src, src_off, (const Point4*)dst, dst_off, init_pose, *params, T_out, iters_out,
+                   mean_err_out, nullptr, nullptr, nullptr, (cudaStream_t)stream, &shard);
 }
 
 extern "C" int r3d_nn_batch(const double* src, const int32_t* src_off, const double* dst, const int32_t* dst_off, int n_pairs,

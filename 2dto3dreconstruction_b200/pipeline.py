@@ -149,3 +149,67 @@ def register_depth_pairs_sharded(depth_src, depth_dst, group=None, **kw):
     T_local = local["T"] if hasattr(local["T"], "is_cuda") else t.from_numpy(local["T"]).cuda()
     T_all = gather_transforms(T_local, B, group)
     return {"T": T_all, "local": local, "shard": (s, e)}
+
+
+def make_exchange(buffer, group=None, stage_through_host=None):
+    """The r3d_exchange_fn of r3d_icp_batch_sharded for a workspace held in the tensor `buffer`: sums the
+    n_doubles float64 at device_buf (a pointer INTO buffer) over the ranks of `group`, in place, with
+    torch.distributed.all_reduce on the current stream (NCCL for CUDA tensors).  With a backend that cannot reduce
+    CUDA tensors (gloo without CUDA support) the slice is staged through the host.  Returns (ctypes callback,
+    python function); keep the callback alive while the library may call it."""
+    import torch.distributed as dist
+    t = C.torch()
+    base = buffer.data_ptr()
+    if stage_through_host is None:
+        stage_through_host = buffer.is_cuda and dist.get_backend(group) != "nccl"
+
+    def exchange(ctx, device_buf, n_doubles, stream):
+        try:
+            off = int(device_buf) - base
+            if off < 0 or off % 8 or off + 8 * int(n_doubles) > buffer.numel():
+                raise ValueError("exchange buffer is not inside the workspace tensor")
+            view = buffer[off:off + 8 * int(n_doubles)].view(t.float64)
+            if stage_through_host:
+                host = view.cpu()
+                dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+                view.copy_(host)
+            else:
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+            return 0
+        except Exception as e:      # an exception must not unwind through the C caller
+            import sys
+            print("r3d exchange failed: %r" % (e,), file=sys.stderr)
+            return 1
+
+    return C.EXCHANGE_FN(exchange), exchange
+
+
+def icp_pair_sharded(A, B, init_pose=None, max_iterations=20, tolerance=0.001, group=None):
+    """utils/icp.py:74-133 for ONE large pair with the queries sharded over the ranks of `group` (SURVEY.md section 8f
+    N4; BASELINE.json configs[3]).  Every rank passes the same (N,3) / (M,3) float64 arrays and gets the same result,
+    bit-identical to utils.icp.icp on one GPU: (T (4,4), mean distance of the last iteration, iters).  partial_set_size
+    is 1.0 (include/r3d_b200.h).  One all-reduce of the virtual-warp moment rows (256 KB - 1 MB) per iteration."""
+    import torch.distributed as dist
+    C.require_device()
+    t = C.torch()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    B = np.ascontiguousarray(B, dtype=np.float64)
+    assert A.ndim == 2 and A.shape[1] == 3 and B.ndim == 2 and B.shape[1] == 3
+    src = ops.pack_xyzw(C.to_device(A))
+    dst = ops.pack_xyzw(C.to_device(B))
+    so, do = ops._offsets([len(A)]), ops._offsets([len(B)])
+    pose = None if init_pose is None else C.to_device(np.ascontiguousarray(init_pose, dtype=np.float64).reshape(1, 16))
+    T = t.empty((1, 4, 4), dtype=t.float64, device="cuda")
+    iters = t.empty(1, dtype=t.int32, device="cuda")
+    err = t.empty(1, dtype=t.float64, device="cuda")
+    prm = C.IcpParams(int(max_iterations), 0, float(tolerance), 1.0, 0.0)
+    L = C.lib()
+    nws = L.r3d_icp_workspace_bytes(1, len(A), len(B))
+    ws = C.workspace(nws)
+    cb, _ = make_exchange(ws, group)
+    C.check(L.r3d_icp_batch_sharded(C.ptr(src), C.ptr(so), C.ptr(dst), C.ptr(do), 1, len(A), len(B), C.ptr(pose),
+                                    ctypes.byref(prm), rank, world, cb, None, C.ptr(T), C.ptr(iters), C.ptr(err), C.ptr(ws),
+                                    ws.numel(), C.stream_ptr()), "r3d_icp_batch_sharded")
+    t.cuda.synchronize()
+    return T[0].cpu().numpy(), float(err.item()), int(iters.item())

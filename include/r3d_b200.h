@@ -139,6 +139,20 @@ int r3d_icp_batch(const double* src, const int32_t* src_off, const double* dst, 
                   int32_t* last_idx, double* last_dist, uint8_t* last_keep,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/*   Query-sharded ICP of ONE large pair over the GPUs of a box (BASELINE.json configs[3]).
+ *   Every process passes the same clouds and parameters plus its rank; each runs the search of every world-th slice
+ *   of the queries and calls `exchange` once per iteration on a device buffer of n_doubles float64 that must be
+ *   SUMMED IN PLACE over all ranks, ordered on `stream` (an NCCL all-reduce).  Each element is non-zero on exactly
+ *   one rank, so the sums are exact and T_out / iters_out / mean_err_out are bit-identical on every rank and to
+ *   r3d_icp_batch on one GPU.  partial_set_size must be 1.0 (the top-fraction selection would need a distributed
+ *   k-th select) and n_pairs 1 (batches are sharded by pair: no exchange at all).  exchange returns 0 on success. */
+typedef int (*r3d_exchange_fn)(void* ctx, void* device_buf, size_t n_doubles, void* stream);
+int r3d_icp_batch_sharded(const double* src, const int32_t* src_off, const double* dst, const int32_t* dst_off,
+                          int n_pairs, int max_src, int max_dst, const double* init_pose, const r3d_icp_params* params,
+                          int rank, int world, r3d_exchange_fn exchange, void* exchange_ctx,
+                          double* T_out, int32_t* iters_out, double* mean_err_out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * K4A  2-D homography RANSAC scoring, reference-exact
  *   replaces the body of the hypothesis loop of utils/homography_utils/q9.py:146-210:

@@ -83,3 +83,43 @@ def test_q9_host_side_dlt_matches_oracle():
     A = q9.make_homography_LS_matrix(ms)
     assert np.array_equal(A, O.dlt_design([O.Match(*m) for m in ms]))
     assert np.array_equal(q9.solve_homography_LS_matrix(A), O.dlt_solve(A))
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    """The r3d_exchange_fn built by pipeline.make_exchange, called the way the library calls it (through the ctypes
+    callback, with a pointer into the workspace tensor), on CPU tensors over gloo: every rank owns the rows
+    r = rank (mod world) of a row table, the others are zero, and after the exchange all ranks hold the full table
+    bit for bit -- the property the query-sharded ICP relies on."""
+    sys.path.insert(0, ROOT)
+    import ctypes
+    import importlib
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
+    rows = 2048
+    full = torch.from_numpy(np.random.default_rng(5).normal(size=(rows, 16)) * 1e6)       # every rank regenerates the truth
+    ws = torch.zeros(4096 + rows * 16 * 8, dtype=torch.uint8)                              # the "workspace": table at byte 1024
+    table = ws[1024:1024 + rows * 16 * 8].view(torch.float64).view(rows, 16)
+    table[rank::world] = full[rank::world]
+    cb, fn = pipeline.make_exchange(ws, None)
+    rc = cb(None, ctypes.c_void_p(ws.data_ptr() + 1024), rows * 16, None)
+    ok = rc == 0 and np.array_equal(table.numpy(), full.numpy()) and not ws[:1024].any() and not ws[1024 + rows * 16 * 8:].any()
+    # a pointer outside the buffer must be reported as a failure, not raise through the C caller
+    bad = cb(None, ctypes.c_void_p(ws.data_ptr() + ws.numel()), 16, None)
+    ok = ok and bad != 0
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_icp_exchange_callback_gloo(tmp_path, world):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
