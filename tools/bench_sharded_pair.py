@@ -63,6 +63,6 @@ if world > 1:
     same = all(torch.equal(x, lst[0]) for x in lst)
 if rank == 0:
     print("gpus %d: %d points, 30 iterations: %.2f ms per registration incl. H2D of both clouds (best of 3, max over ranks); "
-          "mean_err %.6f; identical on all ranks: %s; T[0] = %s" % (world, len(A_h), best, err, same, np.array2string(T[0], precision=12)), flush=True)
+          "mean_err %.6f; identical on all ranks: %s; T[0] = %s" % (world, len(A_h), best, err, same, np.array2string(T[0], precision=12).replace("\n", " ")), flush=True)
 if world > 1:
     dist.destroy_process_group()
