@@ -30,6 +30,7 @@ flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def timed(fn, reps=5, warm=2, flush=True):
+    reps, warm = int(os.environ.get("BK_REPS", reps)), int(os.environ.get("BK_WARM", warm))      # 1 / 0 under ncu
     ts = []
     for k in range(warm + reps):
         if flush:
