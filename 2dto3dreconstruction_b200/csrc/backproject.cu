@@ -116,8 +116,11 @@ __device__ __forceinline__ double div_markstein(double n, double b, double rb) {
     return fma(e, rb, q);
 }
 
+#ifndef R3D_BP_MIN_CTAS
+#define R3D_BP_MIN_CTAS 1
+#endif
 template <typename T, int MODE, int LAYOUT, bool FASTDIV>
-__global__ void __launch_bounds__(BP_THREADS)
+__global__ void __launch_bounds__(BP_THREADS, R3D_BP_MIN_CTAS)
 bp_write(const T* __restrict__ depth, int hw, int width, int tiles_per_frame, double fx, double fy, double cx,
          double cy, double zscale, const int32_t* __restrict__ tile_base, const int32_t* __restrict__ frame_offsets,
          void* __restrict__ out) {

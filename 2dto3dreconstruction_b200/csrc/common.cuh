@@ -78,17 +78,28 @@ __device__ __forceinline__ Point4 load_point(const Point4* p) {
     return r;
 }
 
-__device__ __forceinline__ void store_point(Point4* p, double x, double y, double z, int32_t idx) {
+// One 32-byte record = one 256-bit store (sm_100: STG.E.256; the record is 32-byte aligned).  R3D_STORE256=0 falls
+// back to two 128-bit stores.
+#ifndef R3D_STORE256
+#define R3D_STORE256 1
+#endif
+__device__ __forceinline__ void store_record(Point4* p, double x, double y, double z, double w) {
+#if R3D_STORE256
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "d"(w) : "memory");
+#else
     double2* q = reinterpret_cast<double2*>(p);
     q[0] = make_double2(x, y);
-    q[1] = make_double2(z, __longlong_as_double((long long)(uint32_t)idx));
+    q[1] = make_double2(z, w);
+#endif
+}
+
+__device__ __forceinline__ void store_point(Point4* p, double x, double y, double z, int32_t idx) {
+    store_record(p, x, y, z, __longlong_as_double((long long)(uint32_t)idx));
 }
 
 // tag = cloud index (low word) | a second index (high word); load_point / consider() read the low word only
 __device__ __forceinline__ void store_point_tagged(Point4* p, double x, double y, double z, int32_t idx, int32_t hi) {
-    double2* q = reinterpret_cast<double2*>(p);
-    q[0] = make_double2(x, y);
-    q[1] = make_double2(z, __hiloint2double(hi, idx));
+    store_record(p, x, y, z, __hiloint2double(hi, idx));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
