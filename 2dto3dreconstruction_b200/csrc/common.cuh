@@ -65,11 +65,23 @@ struct __align__(32) Point4 {      // one cloud point: xyz + the point's index i
     int32_t pad;
 };
 
-__device__ __forceinline__ Point4 load_point(const Point4* p) {
-    // two 16-byte loads (the struct is 32-byte aligned)
+// One 32-byte record = one 256-bit read-only load (sm_100: LDG.E.256.CONSTANT).  R3D_LOAD256=0: two 128-bit loads.
+#ifndef R3D_LOAD256
+#define R3D_LOAD256 1
+#endif
+__device__ __forceinline__ void load_record(const void* p, double2& a, double2& b) {
+#if R3D_LOAD256
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y) : "l"(p));
+#else
     const double2* q = reinterpret_cast<const double2*>(p);
-    double2 a = __ldg(q);
-    double2 b = __ldg(q + 1);
+    a = __ldg(q);
+    b = __ldg(q + 1);
+#endif
+}
+
+__device__ __forceinline__ Point4 load_point(const Point4* p) {
+    double2 a, b;
+    load_record(p, a, b);
     Point4 r;
     r.x = a.x; r.y = a.y; r.z = b.x;
     long long w = __double_as_longlong(b.y);

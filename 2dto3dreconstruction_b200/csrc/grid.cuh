@@ -80,9 +80,8 @@ struct Best {
 };
 
 __device__ __forceinline__ void consider(Best& b, const Point4* __restrict__ pts, int k, double qx, double qy, double qz) {
-    const double2* p = reinterpret_cast<const double2*>(pts + k);
-    double2 xy = __ldg(p);
-    double2 zw = __ldg(p + 1);
+    double2 xy, zw;
+    load_record(pts + k, xy, zw);
     double dx = qx - xy.x, dy = qy - xy.y, dz = qz - zw.x;
     double d2 = dx * dx + dy * dy + dz * dz;
     int idx = (int)(__double_as_longlong(zw.y) & 0xffffffffll);

@@ -280,11 +280,7 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 if (ex <= tc) seg += step;
             }
             const uint32_t pos = __shfl_sync(FULL, s, seg) + (tc - __shfl_sync(FULL, excl, seg));
-            if (have) {
-                const double2* p = reinterpret_cast<const double2*>(v.pts + pos);
-                xy = __ldg(p);
-                zw = __ldg(p + 1);
-            }
+            if (have) load_record(v.pts + pos, xy, zw);
         };
         fetch(0u);
         for (uint32_t t0 = 0; t0 < total; t0 += 32) {
@@ -387,8 +383,8 @@ __device__ __forceinline__ Best far_query_search(int owner, const Best& seed, co
             const uint32_t s0 = __ldg(v.block_first + b0 + j), e0 = __ldg(v.block_first + b0 + j + len);
             R3D_STAT(10, (e0 - s0 + 31) / 32);
             for (uint32_t k = s0 + (uint32_t)lane; k < e0; k += 32) {
-                const double2* p = reinterpret_cast<const double2*>(v.pts + k);
-                const double2 xy = __ldg(p), zw = __ldg(p + 1);
+                double2 xy, zw;
+                load_record(v.pts + k, xy, zw);
                 const double ex = ax - xy.x, ey = ay - xy.y, ez = az - zw.x;
                 const double d2 = ex * ex + ey * ey + ez * ez;
                 const int idx = __double2loint(zw.y);
