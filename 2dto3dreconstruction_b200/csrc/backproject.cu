@@ -250,6 +250,7 @@ extern "C" int r3d_backproject(const void* depth, int depth_dtype, int frames, i
     if (!depth || !out_points || !out_offsets || frames <= 0 || height <= 0 || width <= 0) return R3D_ERR_INVALID;
     if ((int64_t)frames * height * width > 0x7fffffffll) return R3D_ERR_INVALID;
     if (frames > 65535) return R3D_ERR_INVALID;
+    if (out_layout == R3D_POINTS_XYZW && (((uintptr_t)out_points) & 31)) return R3D_ERR_INVALID;      // 256-bit stores
     cudaStream_t st = (cudaStream_t)stream;
     switch (depth_dtype) {
         case R3D_DEPTH_U16:

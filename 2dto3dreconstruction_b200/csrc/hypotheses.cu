@@ -143,6 +143,7 @@ using namespace r3d;
 extern "C" int r3d_rigid_hypotheses(const double* P, const double* Q, int n_pts, const int32_t* samples, int n_hyp,
                                     double* T_out, int32_t* status_out, void* stream) {
     if (!P || !Q || !samples || !T_out || n_pts <= 0 || n_hyp <= 0) return R3D_ERR_INVALID;
+    if ((((uintptr_t)P) & 31) || (((uintptr_t)Q) & 31)) return R3D_ERR_INVALID;      // xyzw records are read with 256-bit loads
     R3D_LAUNCH(rigid_hyp_kernel, (n_hyp + 127) / 128, 128, 0, (cudaStream_t)stream, (const Point4*)P, (const Point4*)Q, n_pts,
                samples, n_hyp, T_out, status_out);
     return R3D_OK;
@@ -151,6 +152,7 @@ extern "C" int r3d_rigid_hypotheses(const double* P, const double* Q, int n_pts,
 extern "C" int r3d_affine_hypotheses(const double* P, const double* Q, int n_pts, const int32_t* samples, int n_hyp,
                                      double* T_out, int32_t* status_out, void* stream) {
     if (!P || !Q || !samples || !T_out || n_pts <= 0 || n_hyp <= 0) return R3D_ERR_INVALID;
+    if ((((uintptr_t)P) & 31) || (((uintptr_t)Q) & 31)) return R3D_ERR_INVALID;      // xyzw records are read with 256-bit loads
     R3D_LAUNCH(affine_hyp_kernel, (n_hyp + 127) / 128, 128, 0, (cudaStream_t)stream, (const Point4*)P, (const Point4*)Q, n_pts,
                samples, n_hyp, T_out, status_out);
     return R3D_OK;

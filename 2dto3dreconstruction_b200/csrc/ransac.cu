@@ -344,6 +344,7 @@ extern "C" int r3d_ransac2d_score(const double* H, const double* H_imag, int n_h
 extern "C" int r3d_ransac3d_score(const double* T, int n_hyp, const double* P, const double* Q, int n_pts, double thresh,
                                   int32_t* counts_out, void* stream) {
     if (!T || !P || !Q || !counts_out || n_hyp <= 0 || n_pts < 0) return R3D_ERR_INVALID;
+    if ((((uintptr_t)P) & 31) || (((uintptr_t)Q) & 31)) return R3D_ERR_INVALID;      // xyzw records: bulk copies / 256-bit loads
     cudaStream_t st = (cudaStream_t)stream;
     R3D_CUDA(cudaMemsetAsync(counts_out, 0, (size_t)n_hyp * sizeof(int32_t), st));
     if (n_pts == 0) return R3D_OK;

@@ -14,7 +14,8 @@
  *   - return value: 0 on success, negative r3d_status on failure (r3d_status_string());
  *   - calls are asynchronous on `stream` unless stated otherwise;
  *   - points are double precision.  "xyz" = packed (n,3) row-major doubles (NumPy layout),
- *     "xyzw" = (n,4) doubles, 32-byte aligned, w unused on input.
+ *     "xyzw" = (n,4) doubles, 32-byte aligned (records move as 256-bit loads/stores; a misaligned pointer
+ *     is rejected with R3D_ERR_INVALID), w unused on input.
  *   - 4x4 transforms are 16 doubles, row-major, acting on column vectors (NumPy layout).
  */
 #ifndef R3D_B200_H
