@@ -3,6 +3,9 @@
     depth_images_to_3d_pts(depth_images, scale=1.)   reconstruct.py:336-344
     depth_images_to_3d_pts_ld(depth_images)          reconstruct.py:347-354
     chain_prefix(transformations)                    reconstruct.py:201-204 (prefix product only)
+    register_consecutive_pairs(point_clouds, rgb_images, depth_images, filter_pts_frac=0.1, partial_set_frac=0.7)
+                                                     reconstruct.py:314-329, the pair loop of trans3d_proc, with the ICP stage
+                                                     of ALL pairs in one batched call
     voxel_down_sample(points, voxel_size)            open3d PointCloud.voxel_down_sample as used at reconstruct.py:220
     merge_point_clouds(point_clouds, transformations, voxel_size=2)
                                                      reconstruct.py:201-220, the merge loop of chain_transformation on
@@ -96,3 +99,31 @@ def merge_point_clouds(point_clouds, transformations, voxel_size=2):
         moved = ops.transform_points(cloud, t.from_numpy(T).cuda())
         combined = ops.voxel_down_sample(t.cat((combined, moved), dim=0), float(voxel_size))
     return combined.cpu().numpy()
+
+
+def register_consecutive_pairs(point_clouds, rgb_images, depth_images, filter_pts_frac=0.1, partial_set_frac=0.7):
+    """The pair loop of trans3d_proc (reconstruct.py:314-329): register image i onto image i-1 for every consecutive
+    pair and return the list of 4x4s (`all_results`).  The global stage of each pair (SIFT, matching, RANSAC, affine
+    fit, sub-sampling) runs pair after pair in the reference's order, so NumPy's global RNG is consumed exactly as by
+    the reference's loop; the ICP refinements, which draw no random numbers, are then run for all pairs in ONE
+    r3d_icp_batch call (a single 13-26 k point pair cannot fill the GPU: tools/batch_small.py).  Every 4x4 is
+    bit-identical to what utils.transformation3d.register_imgs returns for that pair."""
+    from .utils import transformation3d as t3d
+    C.require_device()
+    hs, srcs, dsts = [], [], []
+    for i in range(1, len(point_clouds)):
+        h, src, dst = t3d.global_registration(rgb_images[i], rgb_images[i - 1], depth_images[i], depth_images[i - 1],
+                                              point_clouds[i], point_clouds[i - 1], filter_pts_frac)
+        hs.append(h)
+        srcs.append(np.ascontiguousarray(src, dtype=np.float64))
+        dsts.append(np.ascontiguousarray(dst, dtype=np.float64))
+    if not hs:
+        return []
+    P = len(hs)
+    s = ops.pack_xyzw(C.to_device(np.concatenate(srcs, axis=0)))
+    d = ops.pack_xyzw(C.to_device(np.concatenate(dsts, axis=0)))
+    ns, nd = [len(x) for x in srcs], [len(x) for x in dsts]
+    r = ops.icp_batch(s, ops._offsets(ns), d, ops._offsets(nd), P, max(ns), max(nd), max_iterations=100, tolerance=0.001,
+                      partial_set_size=partial_set_frac)
+    T = r["T"].cpu().numpy()
+    return [np.dot(hs[k], T[k]) for k in range(P)]

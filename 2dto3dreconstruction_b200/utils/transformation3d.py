@@ -96,6 +96,15 @@ def register_imgs(img1_rgb, img2_rgb, img1_depth, img2_depth, scale=1., filter_p
     if img2_pts is None:
         img2_pts = depth_to_voxel(img2_depth, scale=scale)
 
+    h, src, dst = global_registration(img1_rgb, img2_rgb, img1_depth, img2_depth, img1_pts, img2_pts, filter_pts_frac)
+    t, _, _ = icp(src, dst, tolerance=0.001, max_iterations=100, partial_set_size=partial_set_frac)
+    return img1_pts, img2_pts, np.dot(h, t)
+
+
+def global_registration(img1_rgb, img2_rgb, img1_depth, img2_depth, img1_pts, img2_pts, filter_pts_frac):
+    """Everything of register_imgs before its ICP call (utils/transformation3d.py:240-281): SIFT + matching, RANSAC,
+    affine fit on the matched 3-D keypoints, and the two random sub-samples.  Consumes NumPy's global RNG exactly as
+    the reference does.  Returns (h, sub-sampled transformed cloud 1, sub-sampled cloud 2): the ICP inputs."""
     kp1, kp2, matches = generate_keypoints_and_match(img1_rgb, img2_rgb)
     matches = np.array([(m.queryIdx, m.trainIdx) for m in matches])
     _, matches = ransac_loop(img1_rgb, img2_rgb, kp1, kp2, matches)
@@ -114,7 +123,4 @@ def register_imgs(img1_rgb, img2_rgb, img1_depth, img2_depth, scale=1., filter_p
     # same two draws from the global NumPy RNG, same order (utils/transformation3d.py:279-280)
     pts_idx1 = np.random.choice(img2_new.shape[0], int(img2_new.shape[0] * filter_pts_frac), replace=False)
     pts_idx2 = np.random.choice(img2_pts.shape[0], int(img2_pts.shape[0] * filter_pts_frac), replace=False)
-
-    t, _, _ = icp(img2_new[pts_idx1], img2_pts[pts_idx2], tolerance=0.001, max_iterations=100,
-                  partial_set_size=partial_set_frac)
-    return img1_pts, img2_pts, np.dot(h, t)
+    return h, img2_new[pts_idx1], img2_pts[pts_idx2]

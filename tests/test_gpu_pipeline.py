@@ -185,3 +185,44 @@ def test_kitchen_pair_against_the_reference_run():
     assert R.shape == (3, 3) and t.shape == (3, 1)
     np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-10)
     np.testing.assert_allclose(t, g["t"], rtol=0, atol=1e-8)
+
+
+def test_register_consecutive_pairs_batches_the_icp_stage():
+    """The pair loop of trans3d_proc (reconstruct.py:314-329) with the ICP refinements of all pairs in one batched call:
+    every 4x4 must equal, bit for bit, what register_imgs returns pair by pair with the same RNG seed, and the global
+    RNG must end in the same state.  Frames: sofa 1, 2, 1 (two pairs: 2 -> 1 and 1 -> 2)."""
+    import time
+    import warnings
+    pytest.importorskip("cv2")
+    from conftest import load_golden
+    t3d = sub("utils.transformation3d")
+    utils = sub("utils.utils")
+    rec = sub("reconstruct")
+    g = load_golden("sofa_pair")
+    f = load_golden("sofa_frames")
+    order = [0, 1, 0]
+    gray = [f["gray"][k] for k in order]
+    depth = [f["depth"][k] for k in order]
+    clouds = [utils.depth_to_voxel_ld(d) for d in depth]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        seq = []
+        for i in range(1, 3):
+            _, _, h = t3d.register_imgs(gray[i], gray[i - 1], depth[i], depth[i - 1], img1_pts=clouds[i], img2_pts=clouds[i - 1],
+                                        filter_pts_frac=0.05, partial_set_frac=0.7)
+            seq.append(h)
+        t_seq = time.perf_counter() - t0
+        state_seq = np.random.randint(1 << 30)
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        bat = rec.register_consecutive_pairs(clouds, gray, depth, filter_pts_frac=0.05, partial_set_frac=0.7)
+        t_bat = time.perf_counter() - t0
+        state_bat = np.random.randint(1 << 30)
+    print("two pairs: sequential %.3f s, batched ICP stage %.3f s" % (t_seq, t_bat))
+    assert len(bat) == 2 and state_bat == state_seq
+    for a, b in zip(seq, bat):
+        assert np.array_equal(a, b)
+    assert_transform_parity(bat[0], g["final_h"], O.scene_extent(clouds[0]), "first pair vs the reference run")
+    assert rec.register_consecutive_pairs(clouds[:1], gray[:1], depth[:1]) == []
