@@ -285,6 +285,7 @@ gather_kernel(GridWorkspace w, const Point4* __restrict__ dst, const int32_t* __
     const uint32_t* keys = sorted_keys(w, g, pair);
     const uint32_t* vals = w.vals[g.n_passes & 1] + (size_t)pair * w.max_dst;
     Point4* out = w.sorted + (size_t)pair * w.max_dst;
+    float4* packed = w.packed + (size_t)pair * w.max_dst;
     const Point4* src = dst + dst_off[pair];
     uint32_t starts = 0;
 #pragma unroll
@@ -298,6 +299,12 @@ gather_kernel(GridWorkspace w, const Point4* __restrict__ dst, const int32_t* __
             store_point_tagged(out + i, p.x, p.y, p.z, (int32_t)v, (int32_t)i);
             const uint32_t k = keys[i];
             starts += (i == 0) || ((keys[i - 1] >> 6) != (k >> 6));
+            // fp32 copy relative to the block's origin (tile_search.cuh stages these records by bulk copy)
+            const uint32_t blk = k >> 6;
+            const int cbx = (int)(blk % (uint32_t)g.bx), cby = (int)((blk / (uint32_t)g.bx) % (uint32_t)g.by),
+                      cbz = (int)(blk / ((uint32_t)g.bx * (uint32_t)g.by));
+            packed[i] = make_float4((float)(p.x - block_origin(g.ox, 4 * cbx, g.cell)), (float)(p.y - block_origin(g.oy, 4 * cby, g.cell)),
+                                    (float)(p.z - block_origin(g.oz, 4 * cbz, g.cell)), __int_as_float((int)v));
         }
     }
     starts = __reduce_add_sync(0xffffffffu, starts);
@@ -487,6 +494,7 @@ size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_ds
     w.vals[1] = a.take<uint32_t>(P * M);
     w.hist = a.take<uint32_t>(P * 256 * w.tiles);
     w.sorted = a.take<Point4>(P * M);
+    w.packed = a.take<float4>(P * M);
     w.tile_cnt = a.take<uint32_t>(P * w.tiles);
     w.hash = a.take<uint2>(P * slots);
     w.block_key = a.take<uint32_t>(P * M);

@@ -1,12 +1,13 @@
 // K2 query + K3: the ICP loop of utils/icp.py:74-133, batched over pairs, entirely on the device.
 //
 // Per iteration (no host round trip; converged pairs turn into early-exit CTAs):
-//   nn_kernel        q = T_cum * a (fp64), exact NN on the sparse-block grid, one warp per 32
-//                    spatially adjacent queries (coop_search.cuh; the source cloud is sorted by
-//                    cell key once, before the loop).  Iterations >= 2 seed the upper bound with
-//                    the previous neighbour (the cloud moves little between iterations, so the
-//                    search box is ~1-2 cells wider than the warp's footprint).  With
-//                    partial_set_size == 1 the 16 Kabsch moments are reduced in the same kernel.
+//   nn_query_kernel  q = T_cum * a (fp64), exact NN on the sparse-block grid, one warp per 32
+//                    spatially adjacent queries (tile_search.cuh: blocks staged into shared memory
+//                    by TMA, per-lane walk, fp32 filter + fp64 decision; the source cloud is sorted
+//                    by cell key once, before the loop).  Iterations >= 2 seed the upper bound with
+//                    the previous neighbour and skip the search altogether when the neighbour
+//                    provably cannot change.  With partial_set_size == 1 the 16 Kabsch moments are
+//                    reduced in the same kernel.
 //   sel_hist/pick    (partial < 1) radix-select of the cutoff-th smallest squared distance
 //                    = np.argpartition(distances, cutoff-1)[:cutoff], utils/icp.py:109-110
 //   moments_kernel   (partial < 1) moments over the kept correspondences
@@ -14,14 +15,25 @@
 //                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126)
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
-#include "lean_search.cuh"
-#include <cstdlib>
+#include "tile_search.cuh"
 #include <mutex>
 #include <vector>
 
 namespace r3d {
 
 constexpr int NN_THREADS = 128;
+// resident CTAs per SM the kernel is compiled for: the lean search is latency bound and wants 8 (64 registers);
+// the tile search holds ~8.6 KB of staging per warp
+#ifndef R3D_LEAN_MIN_CTAS
+#define R3D_LEAN_MIN_CTAS 8
+#endif
+#ifndef R3D_TILE_MIN_CTAS
+#define R3D_TILE_MIN_CTAS 5
+#endif
+// partial-set selection (radix select, below): passes x bins of the per-pair histograms in the workspace
+constexpr int SEL_PASSES = 6;
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_TILE = 4096;      // keys per CTA of the histogram kernel
 constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent nn kernel (see nn_kernel) ...
 constexpr int NN_VWARPS_BIG = 8192;  // ... and for a pair of more than NN_VWARPS_BIG_FROM source points: a single large pair must
 constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A function of the pair alone, so batching stays irrelevant.
@@ -77,17 +89,13 @@ struct IcpWorkspace {
     uint32_t* shist;       // [pair][256][src radix tiles]
     int src_rtiles;
     Point4* src_sorted;    // [pair][max_src]  source cloud in cell-key order, idx = original index
-    uint32_t* seg_tile_cnt; // [pair][seg_tiles]
-    int seg_tiles;
-    uint32_t* seg_start;   // [pair][max_src + 1]  first sorted query of every source block segment
-    int* n_seg;            // [pair]
-    uint32_t* grp;         // [pair][grp_cap]  query groups: (first sorted query << 6) | count
-    int grp_cap;
-    int* n_grp;            // [pair]
-    int nn_ctas;           // CTAs per pair of the persistent nn kernel
-    int* vw_counter;       // [pair] next virtual warp of the running nn launch (reset by its consumer)
-    int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
-    float* budget;         // [pair][max_src]  lower bound of the distance from the query to every point but its neighbour (lean kernel)
+    int* vw_counter;       // [pair][2] next virtual warp of the running track / search launch (reset by solve_kernel)
+    uint32_t* srch_mask;   // [pair][task_cap]  per task of 32 sorted queries: the lanes whose neighbour list could not settle the query
+    uint32_t* srch_off;    // [pair][task_cap + 1]  exclusive prefix sums of their counts: the queue of the search kernel
+    int task_cap;
+    int4* nbr;             // [pair][max_src]  sorted positions of the query's neighbour list: x = the current nearest neighbour,
+                           //                  y, z, w = the other listed points (entries may repeat x)
+    float* budget;         // [pair][max_src]  lower bound of the distance from the query to every point that is NOT in its list
     double* d2;            // [pair][max_src]
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
@@ -104,7 +112,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
     w.src_rows = w.src_tiles * (NN_THREADS / 32);
-    if (w.src_rows < vwarps_for(max_src)) w.src_rows = vwarps_for(max_src);
+    if (w.src_rows < 2 * vwarps_for(max_src)) w.src_rows = 2 * vwarps_for(max_src);      // fused mode: track rows, then search rows
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
     w.src_desc = a.take<SortDesc>(P);
@@ -115,33 +123,17 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     }
     w.shist = a.take<uint32_t>(P * 256 * w.src_rtiles);
     w.src_sorted = a.take<Point4>(P * max_src);
-    w.seg_tiles = (max_src + 2047) / 2048;
-    w.seg_tile_cnt = a.take<uint32_t>(P * w.seg_tiles);
-    w.seg_start = a.take<uint32_t>(P * ((size_t)max_src + 1));
-    w.n_seg = a.take<int>(P);
-    // worst case: every query alone in its block -> one group per query
-    w.grp_cap = max_src + 1;
-    w.grp = a.take<uint32_t>(P * (size_t)w.grp_cap);
-    w.n_grp = a.take<int>(P);
-    w.vw_counter = a.take<int>(P);
-    {
-        // persistent nn kernel: enough CTAs to fill 148 SMs x 8 resident CTAs over the chunk's pairs,
-        // never more than one warp per task (32 queries; 8 for small pairs)
-        int per_pair = (148 * 8 + n_pairs - 1) / n_pairs;
-        const int per_cta = queries_per_task(max_src) * (NN_THREADS / 32);
-        const int cap = (max_src + per_cta - 1) / per_cta;
-        if (per_pair > cap) per_pair = cap;
-        if (per_pair > vwarps_for(max_src) / (NN_THREADS / 32)) per_pair = vwarps_for(max_src) / (NN_THREADS / 32);
-        if (per_pair < 1) per_pair = 1;
-        w.nn_ctas = per_pair;
-    }
-    w.nn_pos = a.take<int32_t>(P * max_src);
+    w.vw_counter = a.take<int>(P * 2);
+    w.task_cap = (max_src + 31) / 32;
+    w.srch_mask = a.take<uint32_t>(P * (size_t)w.task_cap);
+    w.srch_off = a.take<uint32_t>(P * ((size_t)w.task_cap + 1));
+    w.nbr = a.take<int4>(P * max_src);
     w.budget = a.take<float>(P * max_src);
     w.d2 = a.take<double>(P * max_src);
     w.partial = a.take<double>(P * w.src_rows * 16);
     w.amom = a.take<double>(P * 16);
     w.sel = a.take<SelState>(P);
-    w.sel_hist = a.take<uint32_t>(P * 6 * 2048);      // SEL_PASSES x SEL_BINS
+    w.sel_hist = a.take<uint32_t>(P * SEL_PASSES * SEL_BINS);
     return a.used;
 }
 
@@ -163,8 +155,13 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     s.cutoff = (int)((double)s.n_src * partial_set_size);   // int(N * p), utils/icp.py:109
     s.pad = 0;
     if (s.n_src <= 0 || w.grid.params[pair].n_pts <= 0) s.done = 1;
+    // int(N * p) == 0: the reference fits a transform to ZERO correspondences (means of empty arrays, SVD of NaN ->
+    // LinAlgError).  Here such a pair does nothing and reports iters = 0, a value the loop cannot produce otherwise;
+    // the Python drop-in raises on it (utils/icp.py).
+    if (s.cutoff <= 0 && !s.done) { s.done = 1; s.iters = 0; }
     w.state[pair] = s;
-    w.vw_counter[pair] = 0;
+    w.vw_counter[2 * pair] = 0;
+    w.vw_counter[2 * pair + 1] = 0;
     w.src_desc[pair].n = s.n_src > 0 ? s.n_src : 0;
     w.src_desc[pair].n_passes = w.grid.params[pair].n_passes;
 }
@@ -228,182 +225,6 @@ src_gather_kernel(IcpWorkspace w, const Point4* __restrict__ src, const int32_t*
     store_point(w.src_sorted + (size_t)pair * w.max_src + i, a.x, a.y, a.z, (int32_t)v);
 }
 
-// ---- query groups -----------------------------------------------------------------------------------
-constexpr int SEG_TILE = 2048;
-
-// A segment is the run of sorted source keys of one block (key >> 6).  (Letting segments run across
-// x-adjacent blocks raises lane utilisation from ~55% to ~85% at G = 32 but was measured slightly
-// slower: the union boxes grow in step.)
-__device__ __forceinline__ bool segment_starts(uint32_t prev_key, uint32_t key, uint32_t /*bx*/) {
-    return (key >> 6) != (prev_key >> 6);
-}
-
-__global__ void __launch_bounds__(256)
-seg_count_kernel(IcpWorkspace w) {
-    const int pair = blockIdx.y, tile = blockIdx.x;
-    const int n = w.state[pair].n_src;
-    if (tile * SEG_TILE >= n) return;
-    const uint32_t* keys = w.skeys[w.src_desc[pair].n_passes & 1] + (size_t)pair * w.max_src;
-    const uint32_t bx = (uint32_t)w.grid.params[pair].bx;
-    int c = 0;
-#pragma unroll
-    for (int r = 0; r < SEG_TILE / 256; r++) {
-        const int i = tile * SEG_TILE + r * 256 + threadIdx.x;
-        if (i < n) c += (i == 0) || segment_starts(keys[i - 1], keys[i], bx);
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
-    __shared__ int sw[8];
-    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int k = 0; k < 8; k++) t += sw[k];
-        w.seg_tile_cnt[(size_t)pair * w.seg_tiles + tile] = (uint32_t)t;
-    }
-}
-
-// exclusive scan of n (<= a few hundred thousand) uint32 by one CTA of 1024 threads; returns the total
-__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t* data, int n) {
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int start = 0; start < n; start += 1024) {
-        const int i = start + threadIdx.x;
-        const uint32_t v = (i < n) ? data[i] : 0u;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tot[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t t = warp_tot[lane];
-            uint32_t ts = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
-                if (lane >= o) ts += y;
-            }
-            warp_tot[lane] = ts - t;
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_tot[warp] + x - v;
-        if (i < n) data[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    return carry;
-}
-
-__global__ void __launch_bounds__(1024)
-seg_scan_kernel(IcpWorkspace w) {
-    const int pair = blockIdx.x;
-    const int n = w.state[pair].n_src;
-    const int tiles = (n + SEG_TILE - 1) / SEG_TILE;
-    const uint32_t total = cta_exclusive_scan(w.seg_tile_cnt + (size_t)pair * w.seg_tiles, tiles);
-    if (threadIdx.x == 0) {
-        w.n_seg[pair] = (int)total;
-        w.seg_start[(size_t)pair * (w.max_src + 1) + total] = (uint32_t)n;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-seg_assign_kernel(IcpWorkspace w) {
-    const int pair = blockIdx.y, tile = blockIdx.x;
-    const int n = w.state[pair].n_src;
-    if (tile * SEG_TILE >= n) return;
-    const uint32_t* keys = w.skeys[w.src_desc[pair].n_passes & 1] + (size_t)pair * w.max_src;
-    const uint32_t bx = (uint32_t)w.grid.params[pair].bx;
-    constexpr int NW = 8, ROUNDS = SEG_TILE / 256;
-    __shared__ uint32_t cnt[ROUNDS * NW];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned ballots[ROUNDS];
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        const int i = tile * SEG_TILE + r * 256 + threadIdx.x;
-        bool st = false;
-        if (i < n) st = (i == 0) || segment_starts(keys[i - 1], keys[i], bx);
-        ballots[r] = __ballot_sync(0xffffffffu, st);
-        if (lane == 0) cnt[r * NW + warp] = __popc(ballots[r]);
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t a = cnt[2 * lane], b = cnt[2 * lane + 1], sab = a + b;
-        uint32_t x = sab;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        cnt[2 * lane] = x - sab;
-        cnt[2 * lane + 1] = x - sab + a;
-    }
-    __syncthreads();
-    const uint32_t base = w.seg_tile_cnt[(size_t)pair * w.seg_tiles + tile];
-    uint32_t* seg_start = w.seg_start + (size_t)pair * (w.max_src + 1);
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        if (!((ballots[r] >> lane) & 1u)) continue;
-        const int i = tile * SEG_TILE + r * 256 + threadIdx.x;
-        seg_start[base + cnt[r * NW + warp] + __popc(ballots[r] & ((1u << lane) - 1u))] = (uint32_t)i;
-    }
-}
-
-// one CTA per pair: groups per segment = ceil(size / G); exclusive scan; write the group table.
-// entry = (first sorted query << 6) | count, count in 1..32
-__global__ void __launch_bounds__(1024)
-seg_groups_kernel(IcpWorkspace w, int G) {
-    const int pair = blockIdx.x;
-    const int nseg = w.n_seg[pair];
-    const uint32_t* seg_start = w.seg_start + (size_t)pair * (w.max_src + 1);
-    uint32_t* table = w.grp + (size_t)pair * w.grp_cap;
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int start = 0; start < nseg; start += 1024) {
-        const int j = start + threadIdx.x;
-        uint32_t s0 = 0, sz = 0;
-        if (j < nseg) { s0 = seg_start[j]; sz = seg_start[j + 1] - s0; }
-        const uint32_t v = (sz + G - 1) / G;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tot[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t t = warp_tot[lane];
-            uint32_t ts = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
-                if (lane >= o) ts += y;
-            }
-            warp_tot[lane] = ts - t;
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_tot[warp] + x - v;
-        for (uint32_t k = 0; k < v; k++) {
-            const uint32_t first = s0 + k * G;
-            const uint32_t c = min((uint32_t)G, sz - k * G);
-            table[excl + k] = (first << 6) | c;
-        }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) w.n_grp[pair] = (int)carry;
-}
-
 // ---- per-warp reduction of 16 doubles per lane (no CTA barrier) --------------------------------------
 // `scratch` is >= 16*33 doubles of shared memory owned by the warp.  Rows are skewed by one double
 // so that the 16 row-summing lanes hit distinct banks.  Fixed summation order: deterministic.
@@ -462,143 +283,215 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
 }
 
 // ---- nearest neighbour ----------------------------------------------------------------------------
-// Persistent kernel: grid (nn_ctas, pairs).  A warp repeatedly takes 32/G consecutive query groups.
-#ifndef R3D_NN_MIN_CTAS
-#define R3D_NN_MIN_CTAS 4
+// One ICP iteration's correspondence step is three launches (two in the first iteration):
+//   nn_track_kernel   (iterations >= 2) every query against its NEIGHBOUR LIST -- the four points a search ranked
+//                     nearest, kept per query -- in fp64.  If the best of them is provably still nearer than everything
+//                     that is not listed (test below), it IS the nearest neighbour: the query is settled without a
+//                     search, its moment terms are summed here, and that is the common case after a few iterations.
+//                     The lanes that could not be settled are recorded as one 32-bit mask per task of 32 queries.
+//   srch_scan_kernel  exclusive prefix sums of the masks' popcounts: position of every unsettled query in a queue
+//                     whose order is the sorted-query order (deterministic, no atomics).
+//   nn_query_kernel   the search proper (tile_search.cuh / lean_search.cuh), on the QUEUED queries only, 32 consecutive
+//                     queue entries per warp: a warp is always full of lanes that search, however few queries still do.
+//                     In the first iteration (and for nearest_neighbor()) the queue is the whole cloud.
+// The streaming part (track) is a light kernel at full occupancy; the heavy one (search) runs only where needed.
+//
+// Settling a query without a search.  A search that covered the ball of radius `cover` around the query knows the
+// query's nearest points BY NAME (the seed it started from and the three best other candidates) and a lower bound
+// L of the distance to every point that is NOT named: the fourth-best candidate's fp32 distance rounded inward, or
+// `cover`, whichever is smaller.  L is stored per query (`budget`) next to the names (`nbr`).  If the query later
+// moves by delta in total, every unnamed distance shrinks by at most delta (triangle inequality), so while
+// min over the named points of d(q_now, p) < L - sum(delta) the nearest neighbour is the nearest NAMED point,
+// strictly, whichever of the four that is now.  The per-iteration movement |T_k a - T_{k-1} a| is computed exactly per
+// query and subtracted from the stored bound with outward rounding.  (Round 1 kept one name; the budget then was the
+// gap to the runner-up, a fraction of the point spacing, and was used up while ICP still moved: every lane searched
+// until iteration ~12.  With four names the gap is about one point spacing and most queries settle from iteration ~4.)
+// To have a bound worth keeping, a search asks for a ball a little larger than its bound (`slack`).
+//
+// Virtual warps: work is dealt to vwarps_for(n_src) "virtual warps" per pair and kernel (virtual warp u owns tasks
+// u, u + nvw, ...), handed out dynamically, and each physical warp runs some of them back to back.  The moment sums
+// are kept per VIRTUAL warp (track rows, then search rows), so their summation order -- and therefore every bit of
+// the result -- does not depend on how many CTAs a launch happened to get (chunk size, pairs in flight, GPU count).
+struct LeanTuning {
+    float slack_mult;        // slack = slack_mult * (movement of the query in this iteration) ...
+    float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother) ...
+    float slack_floor_frac;  // ... plus slack_floor_frac * cell
+};
+
+#ifndef R3D_NN_PREFETCH
+#define R3D_NN_PREFETCH 0
 #endif
-// the lean kernel is latency bound: 8 CTAs x 4 warps per SM (64 registers, a few bytes of spill) measured
-// 13% faster than 4 (profiles/r01_nn_sweeps.md)
-#ifndef R3D_LEAN_MIN_CTAS
-#define R3D_LEAN_MIN_CTAS 8
-#endif
-template <int G, bool SEEDED, bool FUSED>
-__global__ void __launch_bounds__(NN_THREADS, R3D_NN_MIN_CTAS)
-nn_kernel(IcpWorkspace w, int write_d2) {
+
+// upper bound of |T_k a - T_{k-1} a| (D = T_k - T_{k-1}) in float, plus the fp64 rounding of the two transformed
+// positions themselves (a few ulps of the coordinates: matters only when coordinates are ~1e9 times the distances)
+__device__ __forceinline__ float query_movement(const double* D, const Point4& a, double qx, double qy, double qz) {
+    const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
+    const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
+    const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
+    return sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
+           __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
+}
+
+// the nearest of the four listed points (fp64, lowest cloud index on ties) and its coordinates
+__device__ __forceinline__ void eval_list(Best& seed, double& sbx, double& sby, double& sbz, const Point4* __restrict__ pts, const int4 nb,
+                                          double qx, double qy, double qz) {
+    consider_xyz(seed, sbx, sby, sbz, pts, nb.x, qx, qy, qz);
+    consider_xyz(seed, sbx, sby, sbz, pts, nb.y, qx, qy, qz);
+    consider_xyz(seed, sbx, sby, sbz, pts, nb.z, qx, qy, qz);
+    consider_xyz(seed, sbx, sby, sbz, pts, nb.w, qx, qy, qz);
+}
+
+constexpr int TRACK_THREADS = 256;
+
+constexpr int TRACK_MIN_CTAS = 4;
+
+template <bool FUSED>
+__global__ void __launch_bounds__(TRACK_THREADS, TRACK_MIN_CTAS)
+nn_track_kernel(IcpWorkspace w, int write_d2) {
     const int pair = blockIdx.y;
-    constexpr int NGW = 32 / G;
-    __shared__ GridParams g;
-    __shared__ double T[12];
-    __shared__ int s_ngrp, s_done;
-    __shared__ Point4 stage[NN_THREADS / 32][COOP_WARP_CAP];     // 6 KB per warp; reused as reduction scratch
+    __shared__ double T[12], D[12], shift[3];
+    __shared__ int s_n, s_done;
+    __shared__ __align__(16) double scratch[TRACK_THREADS / 32][8 * 33];      // moment reduction scratch (two passes of 8)
     if (threadIdx.x == 0) {
-        g = w.grid.params[pair];
-        s_ngrp = w.n_grp[pair];
+        s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
     }
-    if (threadIdx.x < 12) T[threadIdx.x] = w.state[pair].T[threadIdx.x];
+    if (threadIdx.x < 12) {
+        T[threadIdx.x] = w.state[pair].T[threadIdx.x];
+        D[threadIdx.x] = w.state[pair].T[threadIdx.x] - w.state[pair].Tp[threadIdx.x];
+    }
+    if (threadIdx.x < 3) shift[threadIdx.x] = w.grid.params[pair].shift[threadIdx.x];
     __syncthreads();
     if (s_done) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lg = lane & (G - 1);
-    const GridView v = grid_view(w.grid, pair);
-    const uint32_t* table = w.grp + (size_t)pair * w.grp_cap;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Point4* pts = w.grid.sorted + (size_t)pair * w.grid.max_dst;
     const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
-    int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
+    int4* nbr = w.nbr + (size_t)pair * w.max_src;
+    float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
-    const int n_tasks = (s_ngrp + NGW - 1) / NGW;
-    const int nvw = vwarps_for(w.state[pair].n_src);
-    // Work is dealt to vwarps_for(n_src) "virtual warps" per pair (virtual warp u owns tasks u, u + nvw, ...)
-    // and each physical warp runs some of them back to back.  The moment sums are kept per VIRTUAL warp,
-    // so their summation order -- and therefore every bit of the result -- does not depend on how many
-    // CTAs this launch happened to get (chunk size, number of pairs in flight, GPU count).
-    // virtual warps are handed out dynamically (which physical warp runs one does not matter)
-    int* vw_counter = w.vw_counter + pair;
+    uint32_t* mask_out = w.srch_mask + (size_t)pair * w.task_cap;
+    const int n_tasks = (s_n + 31) / 32;
+    const int nvw = vwarps_for(s_n);
+    int* vw_counter = w.vw_counter + 2 * pair;
     while (true) {
-    int vw = 0;
-    if (lane == 0) vw = atomicAdd(vw_counter, 1);
-    vw = __shfl_sync(0xffffffffu, vw, 0);
-    if (vw >= nvw) break;
-    double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
-    for (int task = vw; task < n_tasks; task += nvw) {
-        const int gid = task * NGW + lane / G;
-        bool active = false;
-        int i = 0;
-        if (gid < s_ngrp) {
-            const uint32_t e = __ldg(table + gid);
-            active = lg < (int)(e & 63u);
-            i = (int)(e >> 6) + lg;
-        }
-        double qx = 0.0, qy = 0.0, qz = 0.0;
-        Best best;
-        best.d2 = CUDART_INF;
-        best.idx = 0x7fffffff;
-        best.pos = 0;
-        if (active) {
-            const Point4 a = load_point(src + i);
-            qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
-            qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
-            qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-            if (SEEDED) consider(best, v.pts, nn_pos[i], qx, qy, qz);
-        }
-        GroupStage<G> st;
-        st.buf = stage[warp] + (lane / G) * GroupStage<G>::CAP;
-        st.n = 0;
-        coop_search<G>(st, best, v, g, active, qx, qy, qz);
-        if (active) {
-            nn_pos[i] = best.pos;
-            if (!FUSED || write_d2) d2_out[i] = best.d2;
-        }
-        if (FUSED) {
+        int vw = 0;
+        if (lane == 0) vw = atomicAdd(vw_counter, 1);
+        vw = __shfl_sync(0xffffffffu, vw, 0) * w.shard_world + w.shard_rank;      // (1, 0 unless the queries are sharded over GPUs)
+        if (vw >= nvw) break;
+        double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
+        for (int task = vw; task < n_tasks; task += nvw) {
+            const int i = task * 32 + lane;
+            const bool active = i < s_n;
+            bool settled = false;
             double m[16];
 #pragma unroll
             for (int k = 0; k < 16; k++) m[k] = 0.0;
             if (active) {
-                const Point4 b = load_point(v.pts + best.pos);
-                accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
-                                b.z - g.shift[2], sqrt(best.d2));
+                const Point4 a = load_point(src + i);
+                const int4 nb = nbr[i];
+                const float bound = budget[i];
+                const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
+                const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
+                const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
+                Best seed;
+                seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
+                double bx = 0.0, by = 0.0, bz = 0.0;
+                eval_list(seed, bx, by, bz, pts, nb, qx, qy, qz);
+                const float left = __fsub_rd(bound, query_movement(D, a, qx, qy, qz));
+                settled = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
+                if (settled) {
+                    // the same four names, the nearest in front; what is left of the bound
+                    int4 out;
+                    out.x = seed.pos;
+                    out.y = (nb.x != seed.pos) ? nb.x : nb.y;
+                    out.z = (nb.x != seed.pos && nb.y != seed.pos) ? nb.y : nb.z;
+                    out.w = (nb.w != seed.pos) ? nb.w : nb.z;
+                    if (out.x != nb.x) nbr[i] = out;
+                    budget[i] = left;
+                    if (!FUSED || write_d2) d2_out[i] = seed.d2;
+                    if (FUSED)
+                        accumulate_pair(m, qx - shift[0], qy - shift[1], qz - shift[2], bx - shift[0], by - shift[1], bz - shift[2],
+                                        sqrt(seed.d2));
+                }
             }
-            acc += warp_reduce16(m, reinterpret_cast<double*>(stage[warp]));
+            const unsigned unsettled = __ballot_sync(0xffffffffu, active && !settled);
+            if (lane == 0) mask_out[task] = unsettled;
+            if (FUSED) acc += warp_reduce16_small(m, scratch[warp]);
         }
-    }
-    // every virtual warp writes its row (zeros if it had no task): solve_kernel sums vwarps_for(n_src) rows
-    if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
+        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
     }
 }
 
-// Lean variant (lean_search.cuh): a task is 32 consecutive queries of the sorted source cloud; no
-// group table.  Same virtual-warp scheme, so the moment sums are independent of the launch geometry.
-//
-// Skipping searches that cannot change the answer.  When a seeded search ends with the seed p still the
-// nearest point, it also knows a lower bound L2 of the distance to every OTHER point (the runner-up among
-// the evaluated points, or the radius it covered, whichever is smaller); that bound is the query's stored
-// `budget`.  If the query later moves by delta in total, every other distance shrinks by at most delta
-// (triangle inequality), so while d(q_now, p) < L2 - sum(delta) the neighbour is still p, strictly, and no
-// search is needed -- only the exact new distance to p, which the seed evaluation computes anyway (a query
-// that moves TOWARDS its neighbour, the usual case in a converging ICP, keeps its budget longer than the
-// symmetric bound L2 - d - 2 sum(delta) > 0 would allow).  The per-iteration movement |T_k a - T_{k-1} a| is
-// computed exactly per query and subtracted from the stored bound with outward rounding.  To have a bound worth keeping, a seeded
-// lane asks for a ball a little larger than its bound (`slack`, proportional to its current movement):
-// costs a few candidates now, saves whole searches once ICP has nearly converged.
-struct LeanTuning {
-    float slack_mult;        // slack = slack_mult * (movement of the query in this iteration) ...
-    float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother)
-};
+// One CTA per pair: srch_off[t] = number of unsettled queries in tasks [0, t), srch_off[n_tasks] = their total.
+__global__ void __launch_bounds__(1024)
+srch_scan_kernel(IcpWorkspace w) {
+    const int pair = blockIdx.x;
+    if (w.state[pair].done) return;
+    const int n_tasks = (w.state[pair].n_src + 31) / 32;
+    const uint32_t* mask = w.srch_mask + (size_t)pair * w.task_cap;
+    uint32_t* off = w.srch_off + (size_t)pair * ((size_t)w.task_cap + 1);
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < n_tasks; start += 1024) {
+        const int t = start + threadIdx.x;
+        const uint32_t v = (t < n_tasks) ? (uint32_t)__popc(mask[t]) : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t tt = warp_tot[lane];
+            uint32_t ts = tt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
+                if (lane >= o) ts += y;
+            }
+            warp_tot[lane] = ts - tt;
+        }
+        __syncthreads();
+        const uint32_t excl = carry + warp_tot[warp] + x - v;
+        if (t < n_tasks) off[t] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[n_tasks] = carry;
+}
 
-// (Packing the lanes that still need a search into full warps through a per-warp queue was tried and
-// measured slower -- 339 vs 302 us per launch: the packed warps span several tasks, so their union boxes
-// grow as fast as the number of searches shrinks; profiles/r01_nn_sweeps.md, sweep_8.)
-#ifndef R3D_NN_PREFETCH
-#define R3D_NN_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int IMPL> struct SearchSmem;
+template <> struct SearchSmem<1> { double2 list[LEAN_WARP_SMEM]; };      // survivors list; never shared with the reduction: its stale slots must stay real points
+template <> struct SearchSmem<2> { TileWarp tile; };
 
-template <bool SEEDED, bool FUSED>
-__global__ void __launch_bounds__(NN_THREADS, R3D_LEAN_MIN_CTAS)
-nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
+// QUEUED = false: the queue is the whole cloud and there are no neighbour lists yet (first iteration, nearest_neighbor());
+// QUEUED = true: the queue of the track kernel; the lanes recompute their query and the nearest listed point (the seed).
+// IMPL selects the search: 2 = tile_search.cuh (default), 1 = lean_search.cuh (round 1's warp-union walk, the
+// cross-check).  Both are exact, so every output bit is the same under either.
+template <int IMPL, bool QUEUED, bool FUSED>
+__global__ void __launch_bounds__(NN_THREADS, IMPL == 2 ? R3D_TILE_MIN_CTAS : R3D_LEAN_MIN_CTAS)
+nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
     __shared__ double T[12], D[12];
-    __shared__ int s_n, s_done;
-    // the grid's base pointers live in shared memory: with 64 registers per thread the compiler would otherwise
-    // recompute these 64-bit addresses inside every loop of the search
+    __shared__ int s_n, s_done, s_nq;
+    // the grid's base pointers live in shared memory: the compiler would otherwise recompute these 64-bit
+    // addresses inside every loop of the search
     __shared__ GridView s_view;
     __shared__ __align__(16) double scratch[NN_THREADS / 32][8 * 33];      // moment reduction scratch (two passes of 8)
-    // survivors list of each warp; never shared with the reduction: its stale slots must stay real points
-    __shared__ double2 lists[NN_THREADS / 32][LEAN_WARP_SMEM];
+    __shared__ __align__(16) SearchSmem<IMPL> ssm[NN_THREADS / 32];
     if (threadIdx.x == 0) {
         g = w.grid.params[pair];
         s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
         s_view = grid_view(w.grid, pair);
+        s_nq = QUEUED ? (int)w.srch_off[(size_t)pair * ((size_t)w.task_cap + 1) + (size_t)((w.state[pair].n_src + 31) / 32)] : w.state[pair].n_src;
     }
     if (threadIdx.x < 12) {
         T[threadIdx.x] = w.state[pair].T[threadIdx.x];
@@ -609,24 +502,33 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GridView& v = s_view;
     const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
-    int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
+    int4* nbr = w.nbr + (size_t)pair * w.max_src;
     float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
+    const uint32_t* q_mask = w.srch_mask + (size_t)pair * w.task_cap;
+    const uint32_t* q_off = w.srch_off + (size_t)pair * ((size_t)w.task_cap + 1);
+    const int n_tasks32 = (s_n + 31) / 32;
     const int qpt = queries_per_task(s_n);
-    const int n_tasks = (s_n + qpt - 1) / qpt;
+    const int n_tasks = (s_nq + qpt - 1) / qpt;
     const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
-    int* vw_counter = w.vw_counter + pair;
-    list_init(lists[warp], v.pts);
-    unsigned tma_phase = 0;      // parities of the warp's two staging mbarriers (lean_search.cuh)
+    int* vw_counter = w.vw_counter + 2 * pair + 1;
+    unsigned phase = 0;      // parity of the warp's staging mbarrier(s)
+    if constexpr (IMPL == 1) {
+        list_init(ssm[warp].list, v.pts);
 #if R3D_LEAN_TMA
-    if (lane == 0) {
-        mbar_init(smem_u32(lists[warp] + 2 * LEAN_LIST_CAP + 128), 1);
-        mbar_init(smem_u32(lists[warp] + 2 * LEAN_LIST_CAP + 128) + 8u, 1);
-    }
-    mbar_init_fence();
-    __syncwarp();
+        if (lane == 0) {
+            mbar_init(smem_u32(ssm[warp].list + 2 * LEAN_LIST_CAP + 128), 1);
+            mbar_init(smem_u32(ssm[warp].list + 2 * LEAN_LIST_CAP + 128) + 8u, 1);
+        }
+        mbar_init_fence();
+        __syncwarp();
 #endif
+    } else {
+        if (lane == 0) mbar_init(smem_u32(&ssm[warp].tile.mbar), 1);
+        mbar_init_fence();
+        __syncwarp();
+    }
     while (true) {
         int vw = 0;
         if (lane == 0) vw = atomicAdd(vw_counter, 1);
@@ -634,97 +536,102 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
         for (int task = vw; task < n_tasks; task += nvw) {
-            const int i = task * qpt + (lane & (qpt - 1));      // qpt < 32: 32 / qpt lanes per query (lean_search)
-            const bool active = i < s_n;
-            const bool primary = lane < qpt;                    // the replica that writes the results
-#if R3D_NN_PREFETCH
-            // The virtual warp's next task is 2048 tasks away: nothing of it is in cache.  Once most lanes skip their
-            // search a task is a chain of dependent loads (query, previous neighbour's position, that point), so ask
-            // for the next task's lines now and for its neighbour points at the end of this task.
-            int pos_next = -1;
-            {
-                const int in = (task + nvw) * qpt + (lane & (qpt - 1));
-                if (task + nvw < n_tasks && in < s_n) {
-                    prefetch_l2(src + in);
-                    if (SEEDED) {
-                        pos_next = nn_pos[in];
-                        prefetch_l2(budget + in);
-                    }
+            const int slot = task * qpt + (lane & (qpt - 1));      // qpt < 32: 32 / qpt lanes per query (replicas)
+            const bool active = slot < s_nq;
+            const bool primary = lane < qpt;                       // the replica that writes the results
+            int i = slot;
+            if (QUEUED && active) {
+                // queue entry `slot` -> sorted query: the task of 32 whose prefix count covers it, then the (r+1)-th set lane
+                int lo = 0, hi = n_tasks32 - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (__ldg(q_off + mid) <= (uint32_t)slot) lo = mid; else hi = mid - 1;
                 }
+                i = lo * 32 + (int)__fns(__ldg(q_mask + lo), 0u, slot - (int)__ldg(q_off + lo) + 1);
             }
-#endif
             double qx = 0.0, qy = 0.0, qz = 0.0;
             Best seed, other;
             seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
             other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
-            float left = 0.0f, slack = 0.0f;      // bound on the other points left after this iteration's movement
-            bool skip = false;
+            double sbx = 0.0, sby = 0.0, sbz = 0.0;      // coordinates of the seed
+            float slack = 0.0f;
             if (active) {
                 const Point4 a = load_point(src + i);
                 qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
                 qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
                 qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-                if (SEEDED) {
-                    consider(seed, v.pts, nn_pos[i], qx, qy, qz);
-                    const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
-                    const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
-                    const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
-                    // rounded up; the last term covers the fp64 rounding of the two transformed positions themselves
-                    // (a few ulps of the coordinates), which matters only when coordinates are ~1e9 times the distances
-                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
-                                        __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
-                    left = __fsub_rd(budget[i], moved);
-                    skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
-                    const float want = moved * tune.slack_mult;
-                    slack = (want <= slack_max) ? want + 1e-4f * slack_max : 0.0f;
+                if (QUEUED) {
+                    eval_list(seed, sbx, sby, sbz, v.pts, nbr[i], qx, qy, qz);
+                    const float want = query_movement(D, a, qx, qy, qz) * tune.slack_mult;
+                    slack = ((want <= slack_max) ? want : 0.0f) + tune.slack_floor_frac * (float)g.cell;
                 }
             }
             R3D_STAT(0, 1);
 #ifdef R3D_NN_STATS
             const long long t_task = clock64();
 #endif
-            float cover = 0.0f;
-            lean_search(lists[warp], tma_phase, seed, other, v, g, active && !skip, qx, qy, qz, slack, cover, qpt);
-            const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
-#ifdef R3D_NN_STATS
-            R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip && primary)));
-            // a skipped lane still evaluates the warp's candidates: none of them may beat its seed
-            R3D_STAT(7, __popc(__ballot_sync(0xffffffffu, active && skip && (other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx)))));
-#endif
+            float cover = 0.0f, lb_other = 0.0f;
+            TileList tl;
+            tl.p1 = tl.p2 = tl.p3 = -1;
+            tl.lb_rest = 0.0f;
+            if constexpr (IMPL == 1) {
+                lean_search(ssm[warp].list, phase, seed, other, v, g, active, qx, qy, qz, slack, cover, qpt);
+                lb_other = sqrtf(__double2float_rd(other.d2));
+            } else {
+                // (the range queue shares the warp's reduction scratch: the two are never live at the same time)
+                static_assert(sizeof(scratch[0]) >= TILE_QUEUE_WORDS * sizeof(uint32_t), "the range queue lives in the reduction scratch");
+                tile_search(ssm[warp].tile, reinterpret_cast<uint32_t*>(scratch[warp]), phase, seed, other, lb_other, tl, v, g, active,
+                            qx, qy, qz, slack, cover, qpt);
+            }
+            const bool seed_wins = !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
 #ifdef R3D_NN_STATS
             R3D_STAT(12, clock64() - t_task);
             R3D_STAT_MAX(13, clock64() - t_task);
 #endif
             const Best best = seed_wins ? seed : other;
             if (active && primary) {
-                nn_pos[i] = best.pos;
                 if (!FUSED || write_d2) d2_out[i] = best.d2;
-                float nb = 0.0f;
-                if (skip) {
-                    nb = left;
-                } else if (SEEDED && seed_wins) {
-                    // lower bound of the distance to any point other than the seed, minus the seed's distance
-                    // (float square roots: the 1e-6 factors cover their rounding)
-                    nb = fminf(sqrtf(__double2float_rd(other.d2)), cover) * 0.999999f;
+                // The list for the next iterations: the neighbour first, then the other points that are known by name.
+                // Everything that is NOT listed must be farther than `bound` (0 = no claim: search again next time).
+                int4 out = make_int4(best.pos, best.pos, best.pos, best.pos);
+                float bound = 0.0f;
+                const bool named = seed_wins || best.pos == tl.p1 || best.pos == tl.p2 || best.pos == tl.p3;
+                if (tl.lb_rest > 0.0f && named) {
+                    // the points a tile search ranked (its seed and p1..p3): every other point is beyond tl.lb_rest
+                    int n = 0;
+                    auto take = [&](int c) {
+                        if (c >= 0 && c != best.pos && n < 3) {
+                            if (n == 0) out.y = c; else if (n == 1) out.z = c; else out.w = c;
+                            n++;
+                        }
+                    };
+                    take(seed.pos); take(tl.p1); take(tl.p2); take(tl.p3);
+                    bound = tl.lb_rest * 0.999999f;
+                } else if (QUEUED && seed_wins) {
+                    // one neighbour known by name: every other point is beyond the nearest of the evaluated ones or the
+                    // radius the search covered (float square roots: the 1e-6 factors cover their rounding)
+                    bound = fminf(lb_other, cover) * 0.999999f;
                 }
-                budget[i] = nb;
+                nbr[i] = out;
+                budget[i] = bound;
             }
-#if R3D_NN_PREFETCH
-            if (SEEDED && pos_next >= 0) prefetch_l2(v.pts + pos_next);
-#endif
             if (FUSED) {
                 double m[16];
 #pragma unroll
                 for (int k = 0; k < 16; k++) m[k] = 0.0;
                 if (active && primary) {
-                    const Point4 b = load_point(v.pts + best.pos);
-                    accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
-                                    b.z - g.shift[2], sqrt(best.d2));
+                    double bx = sbx, by = sby, bz = sbz;      // (the seed's coordinates are still in registers)
+                    if (!seed_wins) {
+                        const Point4 b = load_point(v.pts + best.pos);
+                        bx = b.x; by = b.y; bz = b.z;
+                    }
+                    accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], bx - g.shift[0], by - g.shift[1],
+                                    bz - g.shift[2], sqrt(best.d2));
                 }
                 acc += warp_reduce16_small(m, scratch[warp]);
             }
         }
-        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
+        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)(nvw + vw)) * 16 + lane] = acc;
     }
 }
 
@@ -734,9 +641,6 @@ nn_lean_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
 // kernel over all keys that still match the prefix (shared-memory bins, warp-aggregated, merged into
 // the pair's global bins) followed by a one-CTA-per-pair pick of the bin that holds rank k.
 // = np.argpartition(distances, cutoff - 1)[:cutoff], utils/icp.py:109-110.
-constexpr int SEL_PASSES = 6;
-constexpr int SEL_BINS = 2048;
-constexpr int SEL_TILE = 4096;      // keys per CTA of the histogram kernel
 __host__ __device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 55 : 55 - 11 * pass; }
 __host__ __device__ __forceinline__ int sel_bits(int pass) { return pass == 0 ? 9 : 11; }
 
@@ -953,7 +857,7 @@ moments_kernel(IcpWorkspace w) {
     if (i < s.n_src) {
         // the three streams indexed by i are requested together (one memory latency instead of two before the gather)
         const double d2 = w.d2[(size_t)pair * w.max_src + i];
-        const int pos = w.nn_pos[(size_t)pair * w.max_src + i];
+        const int pos = w.nbr[(size_t)pair * w.max_src + i].x;
         const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
         if (kept(d2, i, s.tau, s.idx_cut)) {
             const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
@@ -998,13 +902,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     const int pair = blockIdx.x;
     PairState* st = w.state + pair;
-    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
+    if (threadIdx.x == 0) { w.vw_counter[2 * pair] = 0; w.vw_counter[2 * pair + 1] = 0; }      // this iteration's query launches have finished
     if (st->done) return;
     __shared__ double sm[SOLVE_THREADS];
     __shared__ double m[16];
     const int n = st->n_src;
     // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32;
+    const int rows = rows_fixed > 0 ? 2 * vwarps_for(n) : (n + 31) / 32;
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -1110,7 +1014,7 @@ export_kernel(IcpWorkspace w, const int32_t* __restrict__ src_off, int32_t* __re
     const int n = st.n_src;
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    if (w.grid.params[pair].n_pts <= 0) {     // empty destination cloud: nothing to match
+    if (w.grid.params[pair].n_pts <= 0 || st.iters == 0) {     // empty destination cloud / cutoff 0 (no search ran): nothing to report
         const size_t o = (size_t)src_off[pair] + i;
         if (out_idx) out_idx[o] = -1;
         if (out_dist) out_dist[o] = CUDART_INF;
@@ -1122,7 +1026,7 @@ export_kernel(IcpWorkspace w, const int32_t* __restrict__ src_off, int32_t* __re
     const size_t o = (size_t)src_off[pair] + a.idx;
     const double d2 = w.d2[(size_t)pair * w.max_src + i];
     if (out_idx) {
-        const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + w.nn_pos[(size_t)pair * w.max_src + i]);
+        const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + w.nbr[(size_t)pair * w.max_src + i].x);
         out_idx[o] = b.idx;
     }
     if (out_dist) out_dist[o] = sqrt_dist ? sqrt(d2) : d2;
@@ -1160,45 +1064,50 @@ struct NnTimer {
 };
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
-static std::atomic<int> g_group_size{32};
+static std::atomic<int> g_nn_impl{2};      // 2 = tile search (tile_search.cuh), 1 = warp-union walk (lean_search.cuh)
+static std::atomic<int> g_force_unfused{0}; // test knob: run partial_set_size == 1 through the select + moments kernels
 
-template <int G>
-static int launch_nn_g(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
-    if (seeded) {
-        if (fused) R3D_LAUNCH((nn_kernel<G, true, true>), grid, NN_THREADS, 0, st, w, write_d2);
-        else R3D_LAUNCH((nn_kernel<G, true, false>), grid, NN_THREADS, 0, st, w, write_d2);
-    } else {
-        if (fused) R3D_LAUNCH((nn_kernel<G, false, true>), grid, NN_THREADS, 0, st, w, write_d2);
-        else R3D_LAUNCH((nn_kernel<G, false, false>), grid, NN_THREADS, 0, st, w, write_d2);
-    }
-    return R3D_OK;
-}
+static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f}, g_slack_floor_frac{0.25e-4f};
 
-static std::atomic<int> g_nn_impl{1};      // 1 = lean walk (lean_search.cuh), 0 = staged lists (coop_search.cuh)
-
-static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f};
-
-static int launch_lean(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+template <int IMPL>
+static int launch_query(IcpWorkspace& w, dim3 grid, bool queued, bool fused, int write_d2, cudaStream_t st) {
     LeanTuning tune;
     tune.slack_mult = g_slack_mult.load();
     tune.slack_max_frac = g_slack_max_frac.load();
-    if (seeded) {
-        if (fused) R3D_LAUNCH((nn_lean_kernel<true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
-        else R3D_LAUNCH((nn_lean_kernel<true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+    tune.slack_floor_frac = g_slack_floor_frac.load();
+    if (queued) {
+        if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        else R3D_LAUNCH((nn_query_kernel<IMPL, true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
     } else {
-        if (fused) R3D_LAUNCH((nn_lean_kernel<false, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
-        else R3D_LAUNCH((nn_lean_kernel<false, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, false, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        else R3D_LAUNCH((nn_query_kernel<IMPL, false, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
     }
     return R3D_OK;
 }
 
-static int launch_nn(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
-    if (g_nn_impl.load() == 1) return launch_lean(w, grid, seeded, fused, write_d2, st);
-    switch (g_group_size.load()) {
-        case 32: return launch_nn_g<32>(w, grid, seeded, fused, write_d2, st);
-        case 16: return launch_nn_g<16>(w, grid, seeded, fused, write_d2, st);
-        default: return launch_nn_g<8>(w, grid, seeded, fused, write_d2, st);
+// Persistent kernels: as many CTAs as are RESIDENT at once (148 SMs x the occupancy the kernel is compiled for)
+// spread over the chunk's pairs -- a CTA that has to wait for a slot would leave its pair without workers while the
+// others run -- and never more than one warp per task.
+static int ctas_per_pair(const IcpWorkspace& w, int resident_per_sm, int threads, int queries_per_task_) {
+    int per_pair = (148 * resident_per_sm) / w.n_pairs;
+    const int per_cta = queries_per_task_ * (threads / 32);
+    const int cap = (w.max_src + per_cta - 1) / per_cta;
+    if (per_pair > cap) per_pair = cap;
+    if (per_pair > vwarps_for(w.max_src) / (threads / 32)) per_pair = vwarps_for(w.max_src) / (threads / 32);
+    return per_pair < 1 ? 1 : per_pair;
+}
+
+// The correspondence step of one iteration (see the comment above nn_track_kernel).  seeded = false: first iteration.
+static int launch_nn(IcpWorkspace& w, bool seeded, bool fused, int write_d2, cudaStream_t st) {
+    const int impl = g_nn_impl.load();
+    if (seeded) {
+        R3D_LAUNCH((fused ? nn_track_kernel<true> : nn_track_kernel<false>), dim3(ctas_per_pair(w, TRACK_MIN_CTAS, TRACK_THREADS, 32), w.n_pairs),
+                   TRACK_THREADS, 0, st, w, write_d2);
+        R3D_LAUNCH(srch_scan_kernel, w.n_pairs, 1024, 0, st, w);
     }
+    const dim3 grid(ctas_per_pair(w, impl == 1 ? R3D_LEAN_MIN_CTAS : R3D_TILE_MIN_CTAS, NN_THREADS, queries_per_task(w.max_src)), w.n_pairs);
+    if (impl == 1) return launch_query<1>(w, grid, seeded, fused, write_d2, st);
+    return launch_query<2>(w, grid, seeded, fused, write_d2, st);
 }
 
 static int sort_source(IcpWorkspace& w, const Point4* src, const int32_t* src_off, cudaStream_t st) {
@@ -1207,13 +1116,6 @@ static int sort_source(IcpWorkspace& w, const Point4* src, const int32_t* src_of
     int rc = radix_sort_pairs(w.skeys, w.svals, w.shist, w.src_desc, w.n_pairs, w.max_src, w.src_rtiles, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(src_gather_kernel, g256, 256, 0, st, w, src, src_off);
-    if (g_nn_impl.load() == 1) return R3D_OK;      // the lean walk takes 32 consecutive queries per task
-    // query groups (never straddling a block)
-    const dim3 gseg(w.seg_tiles, w.n_pairs);
-    R3D_LAUNCH(seg_count_kernel, gseg, 256, 0, st, w);
-    R3D_LAUNCH(seg_scan_kernel, w.n_pairs, 1024, 0, st, w);
-    R3D_LAUNCH(seg_assign_kernel, gseg, 256, 0, st, w);
-    R3D_LAUNCH(seg_groups_kernel, w.n_pairs, 1024, 0, st, w, g_group_size.load());
     return R3D_OK;
 }
 
@@ -1237,24 +1139,25 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
         w.shard_rank = shard->rank;
         w.shard_world = shard->world;
     }
-    const size_t shard_doubles = (size_t)vwarps_for(w.max_src) * 16;      // one pair (checked by the caller): rows [0, nvw)
+    const size_t shard_doubles = (size_t)2 * vwarps_for(w.max_src) * 16;      // one pair (checked by the caller): track rows + search rows
     int rc = grid_build(w.grid, dst, dst_off, prm.cell_size, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(state_init_kernel, (P + 127) / 128, 128, 0, st, w, src_off, init_pose, prm.partial_set_size);
     const dim3 qgrid(w.src_tiles, P);
-    const dim3 nngrid(w.nn_ctas, P);
     rc = sort_source(w, src, src_off, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(src_moments_kernel, qgrid, NN_THREADS, 0, st, w);
     R3D_LAUNCH(src_moments_reduce_kernel, P, SOLVE_THREADS, 0, st, w);
-    const bool fused = prm.partial_set_size >= 1.0 && !getenv("R3D_FORCE_UNFUSED");
+    const bool fused = prm.partial_set_size >= 1.0 && !g_force_unfused.load();
+    // (the first iteration has no track launch: its rows of the moment table must read as zero)
+    if (fused) R3D_CUDA(cudaMemsetAsync(w.partial, 0, (size_t)P * w.src_rows * 16 * sizeof(double), st));
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
     if (!fused) R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * SEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
     for (int it = 0; it < prm.max_iterations; it++) {
         if (sharded) R3D_CUDA(cudaMemsetAsync(w.partial, 0, shard_doubles * sizeof(double), st));
         {
             NnTimer timer(st);
-            rc = launch_nn(w, nngrid, it > 0, fused, fused ? want_d2 : 1, st);
+            rc = launch_nn(w, it > 0, fused, fused ? want_d2 : 1, st);
             if (rc != R3D_OK) return rc;
         }
         if (sharded) {
@@ -1304,7 +1207,7 @@ int nn_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Poi
     if (rc != R3D_OK) return rc;
     {
         NnTimer timer(st);
-        rc = launch_nn(w, dim3(w.nn_ctas, P), false, false, 1, st);
+        rc = launch_nn(w, false, false, 1, st);
         if (rc != R3D_OK) return rc;
     }
     R3D_LAUNCH(export_kernel, dim3((w.max_src + 255) / 256, P), 256, 0, st, w, src_off, out_idx, out_dist, (uint8_t*)nullptr, 1);
@@ -1350,7 +1253,6 @@ extern "C" int r3d_icp_batch_sharded(const double* src, const int32_t* src_off, 
     if (world < 1 || rank < 0 || rank >= world || world > NN_VWARPS || (world > 1 && !exchange)) return R3D_ERR_INVALID;
     if (params->max_iterations < 0 || params->partial_set_size != 1.0) return R3D_ERR_INVALID;      // see include/r3d_b200.h
     if ((((uintptr_t)src) & 31) || (((uintptr_t)dst) & 31)) return R3D_ERR_INVALID;
-    if (g_nn_impl.load() != 1) return R3D_ERR_INVALID;
     IcpWorkspace w;
     int rc = icp_workspace_bind(w, workspace, workspace_bytes, n_pairs, max_src, max_dst);
     if (rc != R3D_OK) return rc;
@@ -1417,18 +1319,15 @@ extern "C" int r3d_nn_stats_read_ext(uint64_t* out16_host, int reset) { return n
 
 extern "C" int r3d_set_option(int option, double value) {
     switch (option) {
-        case R3D_OPT_GROUP_SIZE: {
-            const int gsz = (int)value;
-            if (gsz != 8 && gsz != 16 && gsz != 32) return R3D_ERR_INVALID;
-            g_group_size.store(gsz);
-            return R3D_OK;
-        }
         case R3D_OPT_NN_IMPL: {
             const int impl = (int)value;
-            if (impl != 0 && impl != 1) return R3D_ERR_INVALID;
+            if (impl != 1 && impl != 2) return R3D_ERR_INVALID;
             g_nn_impl.store(impl);
             return R3D_OK;
         }
+        case R3D_OPT_FORCE_UNFUSED:
+            g_force_unfused.store(value != 0.0 ? 1 : 0);
+            return R3D_OK;
         case R3D_OPT_SLACK_MULT:
             if (!(value >= 0.0 && value <= 1.0e6)) return R3D_ERR_INVALID;
             g_slack_mult.store((float)value);
@@ -1436,6 +1335,10 @@ extern "C" int r3d_set_option(int option, double value) {
         case R3D_OPT_SLACK_MAX_FRAC:
             if (!(value >= 0.0 && value <= 64.0)) return R3D_ERR_INVALID;
             g_slack_max_frac.store((float)value);
+            return R3D_OK;
+        case R3D_OPT_SLACK_FLOOR_FRAC:
+            if (!(value >= 0.0 && value <= 64.0)) return R3D_ERR_INVALID;
+            g_slack_floor_frac.store((float)value);
             return R3D_OK;
         case R3D_OPT_CELL_FACTOR:
             if (!(value > 0.05 && value < 100.0)) return R3D_ERR_INVALID;

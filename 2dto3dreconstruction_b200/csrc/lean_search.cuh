@@ -1,7 +1,8 @@
 // Warp-union exact nearest-neighbour search on the sparse-block grid.
 //
-// Same contract as coop_search.cuh (exact NN, lowest-index tie-break, equal to float64 brute
-// force; utils/icp.py:58-71 up to exact ties).  A warp owns 32 consecutive queries of the
+// Contract: exact NN, lowest-index tie-break, equal to float64 brute force (utils/icp.py:58-71 up to
+// exact ties).  This is round 1's search, kept as the cross-check of tile_search.cuh (the default since
+// round 2; select this one with R3D_OPT_NN_IMPL = 1).  A warp owns 32 consecutive queries of the
 // spatially sorted source cloud, shares ONE candidate stream, and every lane evaluates every
 // candidate that survives a box filter:
 //   1. every lane turns its upper bound into a ball and the ball into a box of cells; the warp
@@ -26,7 +27,7 @@
 // handled one query at a time by the whole warp: blocks are pruned by their distance to the query and the
 // survivors scanned 32 points at a time (far_query_search).
 #pragma once
-#include "coop_search.cuh"
+#include "grid.cuh"
 
 // Candidate stream staged into shared memory by cp.async.bulk (1) or by per-lane LDG (0).  The TMA path is
 // correct and tested (build with R3D_LEAN_TMA=1) but measured 15% slower, 333 vs 289 us per launch

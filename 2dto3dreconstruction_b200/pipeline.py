@@ -145,8 +145,15 @@ def register_depth_pairs_sharded(depth_src, depth_dst, group=None, **kw):
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     B = depth_src.shape[0]
     s, e = shard_range(B, rank, world)
-    local = register_depth_pairs(depth_src[s:e], depth_dst[s:e], **kw)
-    T_local = local["T"] if hasattr(local["T"], "is_cuda") else t.from_numpy(local["T"]).cuda()
+    if e > s:
+        local = register_depth_pairs(depth_src[s:e], depth_dst[s:e], **kw)
+        T_local = local["T"] if hasattr(local["T"], "is_cuda") else t.from_numpy(local["T"])
+    else:
+        # fewer pairs than ranks: this rank has nothing to register but must still take part in the collective
+        local = None
+        T_local = t.zeros((0, 4, 4), dtype=t.float64)
+    if dist.get_backend(group) == "nccl" and not T_local.is_cuda:
+        T_local = T_local.cuda()
     T_all = gather_transforms(T_local, B, group)
     return {"T": T_all, "local": local, "shard": (s, e)}
 

@@ -42,7 +42,10 @@ def icp(A, B, init_pose=None, max_iterations=20, tolerance=0.001, partial_set_si
     (1-based, max_iterations + 1 when the tolerance was never met)."""
     A = np.asarray(A)
     B = np.asarray(B)
-    t = C.torch()
+    if max_iterations > 0 and A.shape[0] > 0 and int(A.shape[0] * partial_set_size) == 0:
+        # utils/icp.py:109-117 with cutoff 0: best_fit_transform of two EMPTY sets -> mean of nothing -> SVD of NaN.
+        # The reference fails loudly there; so does the drop-in (the kernels report such a pair with iters = 0).
+        raise np.linalg.LinAlgError("SVD did not converge")
     s = _cloud(A)
     d = _cloud(B)
     pose = None

@@ -27,16 +27,32 @@ def depth_to_voxel(img, scale=1.):
 def homo_rigid_transform_3d(img1_kp, img2_kp):
     """Least-squares 12-dof affine mapping img1_kp -> img2_kp as a 4x4 with last row 0 0 0 1.
     The reference solves the (3K,12) float32 system with lsq_linear/lstsq; the kernel solves the
-    equivalent centred normal equations in fp64.  A rank-deficient (e.g. coplanar) keypoint set, for
-    which lstsq would return its minimum-norm solution, raises instead."""
+    equivalent centred normal equations in fp64.  For a rank-deficient keypoint set (coplanar depth such as
+    a flat wall, fewer than 4 matches) the normal equations are singular and the reference returns lstsq's
+    minimum-norm solution: that degenerate case alone is solved the reference's way on the host (a 12-column
+    system of a few hundred flops), so the drop-in returns what the reference returns instead of raising."""
     p = C.to_device(np.asarray(img1_kp), np.float64)
     q = C.to_device(np.asarray(img2_kp), np.float64)
     if p.dim() != 2 or p.shape[1] != 3 or q.shape != p.shape:
         raise ValueError("expected two (K,3) arrays")
     T, status = ops.affine_fit(p, q)
     if int(status.item()) != 0:
-        raise np.linalg.LinAlgError("homo_rigid_transform_3d: rank-deficient keypoint set")
+        return _min_norm_affine(np.asarray(img1_kp), np.asarray(img2_kp))
     return T.cpu().numpy()
+
+
+def _min_norm_affine(p, q):
+    """The degenerate case of homo_rigid_transform_3d: scipy's unbounded lsq_linear is np.linalg.lstsq(A, b, rcond=-1)
+    on the (3K,12) float32 design matrix of utils/transformation3d.py:133-147 (rows [p 1] in the x, y and z column
+    blocks) and b = img2_kp.flatten() (:163-180)."""
+    K = p.shape[0]
+    ph = np.concatenate((p, np.ones((K, 1))), axis=1)
+    A = np.zeros((3 * K, 12), dtype=np.float32)
+    A[0::3, 0:4] = ph
+    A[1::3, 4:8] = ph
+    A[2::3, 8:12] = ph
+    x = np.linalg.lstsq(A, q.flatten(), rcond=-1)[0]
+    return np.concatenate((x.reshape((3, 4)), np.array([[0, 0, 0, 1]])), axis=0)
 
 
 def get_transformed_points(points, h):

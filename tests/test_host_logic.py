@@ -61,6 +61,46 @@ def test_gather_transforms_gloo(tmp_path, world, n_total):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
 
 
+def _sharded_worker(rank, world, port, n_total, out_dir):
+    """register_depth_pairs_sharded with the device call stubbed out: what is tested is the sharding and the
+    collective, in particular that a rank whose shard is EMPTY (fewer pairs than ranks) still enters the all-gather."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
+    truth = np.random.default_rng(9).normal(size=(n_total, 4, 4))
+    calls = []
+
+    def fake_register(src, dst, **kw):
+        assert src.shape[0] > 0, "the device call must not be made for an empty shard"
+        calls.append(src.shape[0])
+        return {"T": truth[src[:, 0, 0].astype(int)].copy()}
+
+    pipeline.register_depth_pairs = fake_register
+    frames = np.zeros((n_total, 2, 2), np.uint16)
+    frames[:, 0, 0] = np.arange(n_total)                  # the pair index rides in the frame
+    out = pipeline.register_depth_pairs_sharded(frames, frames)
+    s, e = out["shard"]
+    ok = np.array_equal(out["T"].numpy(), truth) and (calls == ([e - s] if e > s else [])) and ((out["local"] is None) == (e == s))
+    with open(os.path.join(out_dir, "rank%d" % rank), "w") as f:
+        f.write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(3, 2), (2, 1), (2, 5)])
+def test_sharded_registration_with_empty_shards_gloo(tmp_path, world, n_total):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_sharded_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
 def test_drop_in_argument_errors_do_not_need_a_gpu():
     r3d = sub("utils.r3d")
     A = np.zeros((5, 3))

@@ -16,14 +16,13 @@ partial = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 group = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 factor = float(sys.argv[5]) if len(sys.argv) > 5 else 2.0
-impl = int(sys.argv[6]) if len(sys.argv) > 6 else 1
+impl = int(sys.argv[6]) if len(sys.argv) > 6 else 2
 warm = int(os.environ.get("WARM", "1"))
 
 import bench  # noqa: E402
 
 pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
 C = importlib.import_module("2dto3dreconstruction_b200._capi")
-C.lib().r3d_set_option(1, float(group))
 C.lib().r3d_set_option(2, factor)
 C.lib().r3d_set_option(3, float(impl))
 a, b = bench.synth_batch_torch(pairs, 0, torch.device("cuda", 0))

@@ -24,7 +24,7 @@ import bench  # noqa: E402
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 partial = float(sys.argv[3]) if len(sys.argv) > 3 else 1.0
-configs = os.environ.get("SWEEP", "0:32:2.0,1:32:2.0,1:16:2.0,1:8:2.0,1:32:1.5,1:32:1.0,1:16:1.0,1:8:1.0,1:32:3.0")
+configs = os.environ.get("SWEEP", "2:32:2.0,1:32:2.0,2:32:1.5,2:32:2.5,2:32:3.0")
 
 pipeline = importlib.import_module("2dto3dreconstruction_b200.pipeline")
 C = importlib.import_module("2dto3dreconstruction_b200._capi")
@@ -45,10 +45,11 @@ for cfg in configs.split(","):
     parts = cfg.split(":")
     impl, group, factor = parts[:3]
     mult, maxfrac = (parts[3], parts[4]) if len(parts) >= 5 else ("8", "0.25")
+    floor = parts[5] if len(parts) >= 6 else "0.000025"
+    assert L.r3d_set_option(7, float(floor)) == 0
     assert L.r3d_set_option(4, float(mult)) == 0
     assert L.r3d_set_option(5, float(maxfrac)) == 0
     assert L.r3d_set_option(3, float(impl)) == 0
-    assert L.r3d_set_option(1, float(group)) == 0
     assert L.r3d_set_option(2, float(factor)) == 0
     out = pipeline.register_depth_pairs(a, b, **kw)
     torch.cuda.synchronize()
@@ -66,16 +67,21 @@ for cfg in configs.split(","):
         ref = T
     dev = float((T - ref).abs().max())
     nq = int(out["n_src"].sum())
-    print("impl %s G %2s factor %s slack %sx<=%s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
+    print("impl %s G %2s factor %s slack %sx<=%s+%s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
           "%.2f G corr/s in kernel | max|T - T0| %.2e err0 %.6f" % (
-              impl, group, factor, mult, maxfrac, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
+              impl, group, factor, mult, maxfrac, floor, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
               nq * n.value / max(ms.value, 1e-9) / 1e6, dev, float(out["mean_err"][0])), flush=True)
     if stats_on:
-        st = (ctypes.c_uint64 * 8)()
-        L.r3d_nn_stats_read(st, 1)
+        sx = (ctypes.c_uint64 * 16)()
+        L.r3d_nn_stats_read_ext(sx, 1)
+        st = list(sx)[:8]
         tasks = max(int(st[0]), 1)
-        print("    per task of 32 queries: rounds %.2f, candidates/lane %.1f, lanes skipped %.2f, lookup rounds %.2f, "
-              "segments %.1f, non-empty %.1f | violated skip bounds: %d" % (
-                  st[1] / tasks, st[2] / tasks, st[3] / tasks, st[4] / tasks, st[5] / tasks, st[6] / tasks, st[7]), flush=True)
+        ev = st[2] / tasks / (32.0 if impl == "2" else 1.0)      # the tile search counts evaluations per lane, summed over the warp
+        print("    per task of 32 queries: rounds %.2f, candidates/lane %.1f, lanes skipped %.2f, lookup rounds / staging passes %.2f, "
+              "segments / block slots %.1f, non-empty / staged %.1f | violated skip bounds: %d" % (
+                  st[1] / tasks, ev, st[3] / tasks, st[4] / tasks, st[5] / tasks, st[6] / tasks, st[7]), flush=True)
+        if impl == "2":
+            print("    tile search: fp64 re-evaluations per query %.2f, records staged per task %.1f" % (
+                sx[14] / tasks / 32.0, sx[15] / tasks), flush=True)
         assert st[7] == 0, "a skipped lane saw a point closer than its seed"
     assert dev < 1e-9, "variants disagree"
