@@ -89,13 +89,9 @@ struct IcpWorkspace {
     uint32_t* shist;       // [pair][256][src radix tiles]
     int src_rtiles;
     Point4* src_sorted;    // [pair][max_src]  source cloud in cell-key order, idx = original index
-    int* vw_counter;       // [pair][2] next virtual warp of the running track / search launch (reset by solve_kernel)
-    uint32_t* srch_mask;   // [pair][task_cap]  per task of 32 sorted queries: the lanes whose neighbour list could not settle the query
-    uint32_t* srch_off;    // [pair][task_cap + 1]  exclusive prefix sums of their counts: the queue of the search kernel
-    int task_cap;
-    int4* nbr;             // [pair][max_src]  sorted positions of the query's neighbour list: x = the current nearest neighbour,
-                           //                  y, z, w = the other listed points (entries may repeat x)
-    float* budget;         // [pair][max_src]  lower bound of the distance from the query to every point that is NOT in its list
+    int* vw_counter;       // [pair] next virtual warp of the running nn launch (reset by its consumer)
+    int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
+    float* budget;         // [pair][max_src]  lower bound of the distance from the query to every point but its neighbour
     double* d2;            // [pair][max_src]
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
@@ -112,7 +108,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
     w.src_rows = w.src_tiles * (NN_THREADS / 32);
-    if (w.src_rows < 2 * vwarps_for(max_src)) w.src_rows = 2 * vwarps_for(max_src);      // fused mode: track rows, then search rows
+    if (w.src_rows < vwarps_for(max_src)) w.src_rows = vwarps_for(max_src);
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
     w.src_desc = a.take<SortDesc>(P);
@@ -123,11 +119,8 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     }
     w.shist = a.take<uint32_t>(P * 256 * w.src_rtiles);
     w.src_sorted = a.take<Point4>(P * max_src);
-    w.vw_counter = a.take<int>(P * 2);
-    w.task_cap = (max_src + 31) / 32;
-    w.srch_mask = a.take<uint32_t>(P * (size_t)w.task_cap);
-    w.srch_off = a.take<uint32_t>(P * ((size_t)w.task_cap + 1));
-    w.nbr = a.take<int4>(P * max_src);
+    w.vw_counter = a.take<int>(P);
+    w.nn_pos = a.take<int32_t>(P * max_src);
     w.budget = a.take<float>(P * max_src);
     w.d2 = a.take<double>(P * max_src);
     w.partial = a.take<double>(P * w.src_rows * 16);
@@ -160,8 +153,7 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     // the Python drop-in raises on it (utils/icp.py).
     if (s.cutoff <= 0 && !s.done) { s.done = 1; s.iters = 0; }
     w.state[pair] = s;
-    w.vw_counter[2 * pair] = 0;
-    w.vw_counter[2 * pair + 1] = 0;
+    w.vw_counter[pair] = 0;
     w.src_desc[pair].n = s.n_src > 0 ? s.n_src : 0;
     w.src_desc[pair].n_passes = w.grid.params[pair].n_passes;
 }
@@ -283,204 +275,46 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
 }
 
 // ---- nearest neighbour ----------------------------------------------------------------------------
-// One ICP iteration's correspondence step is three launches (two in the first iteration):
-//   nn_track_kernel   (iterations >= 2) every query against its NEIGHBOUR LIST -- the four points a search ranked
-//                     nearest, kept per query -- in fp64.  If the best of them is provably still nearer than everything
-//                     that is not listed (test below), it IS the nearest neighbour: the query is settled without a
-//                     search, its moment terms are summed here, and that is the common case after a few iterations.
-//                     The lanes that could not be settled are recorded as one 32-bit mask per task of 32 queries.
-//   srch_scan_kernel  exclusive prefix sums of the masks' popcounts: position of every unsettled query in a queue
-//                     whose order is the sorted-query order (deterministic, no atomics).
-//   nn_query_kernel   the search proper (tile_search.cuh / lean_search.cuh), on the QUEUED queries only, 32 consecutive
-//                     queue entries per warp: a warp is always full of lanes that search, however few queries still do.
-//                     In the first iteration (and for nearest_neighbor()) the queue is the whole cloud.
-// The streaming part (track) is a light kernel at full occupancy; the heavy one (search) runs only where needed.
+// Persistent query kernel: grid (CTAs per pair, pairs); a task is 32 consecutive queries of the sorted source cloud.
+// Work is dealt to vwarps_for(n_src) "virtual warps" per pair (virtual warp u owns tasks u, u + nvw, ...), handed
+// out dynamically, and each physical warp runs some of them back to back.  The moment sums are kept per VIRTUAL
+// warp, so their summation order -- and therefore every bit of the result -- does not depend on how many CTAs
+// this launch happened to get (chunk size, number of pairs in flight, GPU count).
+// IMPL selects the search: 1 = lean_search.cuh (warp-union walk, the default), 2 = tile_search.cuh (blocks staged
+// by TMA, per-lane walk, fp32 filter + fp64 decision).  Both are exact, so every output bit is the same under either.
 //
-// Settling a query without a search.  A search that covered the ball of radius `cover` around the query knows the
-// query's nearest points BY NAME (the seed it started from and the three best other candidates) and a lower bound
-// L of the distance to every point that is NOT named: the fourth-best candidate's fp32 distance rounded inward, or
-// `cover`, whichever is smaller.  L is stored per query (`budget`) next to the names (`nbr`).  If the query later
-// moves by delta in total, every unnamed distance shrinks by at most delta (triangle inequality), so while
-// min over the named points of d(q_now, p) < L - sum(delta) the nearest neighbour is the nearest NAMED point,
-// strictly, whichever of the four that is now.  The per-iteration movement |T_k a - T_{k-1} a| is computed exactly per
-// query and subtracted from the stored bound with outward rounding.  (Round 1 kept one name; the budget then was the
-// gap to the runner-up, a fraction of the point spacing, and was used up while ICP still moved: every lane searched
-// until iteration ~12.  With four names the gap is about one point spacing and most queries settle from iteration ~4.)
-// To have a bound worth keeping, a search asks for a ball a little larger than its bound (`slack`).
-//
-// Virtual warps: work is dealt to vwarps_for(n_src) "virtual warps" per pair and kernel (virtual warp u owns tasks
-// u, u + nvw, ...), handed out dynamically, and each physical warp runs some of them back to back.  The moment sums
-// are kept per VIRTUAL warp (track rows, then search rows), so their summation order -- and therefore every bit of
-// the result -- does not depend on how many CTAs a launch happened to get (chunk size, pairs in flight, GPU count).
+// Skipping searches that cannot change the answer.  When a seeded search ends with the seed p still the
+// nearest point, it also knows a lower bound L2 of the distance to every OTHER point (the runner-up among
+// the evaluated points, or the radius it covered, whichever is smaller); that bound is the query's stored
+// `budget`.  If the query later moves by delta in total, every other distance shrinks by at most delta
+// (triangle inequality), so while d(q_now, p) < L2 - sum(delta) the neighbour is still p, strictly, and no
+// search is needed -- only the exact new distance to p, which the seed evaluation computes anyway (a query
+// that moves TOWARDS its neighbour, the usual case in a converging ICP, keeps its budget longer than the
+// symmetric bound L2 - d - 2 sum(delta) > 0 would allow).  The per-iteration movement |T_k a - T_{k-1} a| is
+// computed exactly per query and subtracted from the stored bound with outward rounding.  To have a bound worth keeping, a seeded
+// lane asks for a ball a little larger than its bound (`slack`, proportional to its current movement):
+// costs a few candidates now, saves whole searches once ICP has nearly converged.
 struct LeanTuning {
     float slack_mult;        // slack = slack_mult * (movement of the query in this iteration) ...
-    float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother) ...
-    float slack_floor_frac;  // ... plus slack_floor_frac * cell
+    float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother)
 };
 
 #ifndef R3D_NN_PREFETCH
 #define R3D_NN_PREFETCH 0
 #endif
-
-// upper bound of |T_k a - T_{k-1} a| (D = T_k - T_{k-1}) in float, plus the fp64 rounding of the two transformed
-// positions themselves (a few ulps of the coordinates: matters only when coordinates are ~1e9 times the distances)
-__device__ __forceinline__ float query_movement(const double* D, const Point4& a, double qx, double qy, double qz) {
-    const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
-    const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
-    const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
-    return sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
-           __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
-}
-
-// the nearest of the four listed points (fp64, lowest cloud index on ties) and its coordinates
-__device__ __forceinline__ void eval_list(Best& seed, double& sbx, double& sby, double& sbz, const Point4* __restrict__ pts, const int4 nb,
-                                          double qx, double qy, double qz) {
-    consider_xyz(seed, sbx, sby, sbz, pts, nb.x, qx, qy, qz);
-    consider_xyz(seed, sbx, sby, sbz, pts, nb.y, qx, qy, qz);
-    consider_xyz(seed, sbx, sby, sbz, pts, nb.z, qx, qy, qz);
-    consider_xyz(seed, sbx, sby, sbz, pts, nb.w, qx, qy, qz);
-}
-
-constexpr int TRACK_THREADS = 256;
-
-constexpr int TRACK_MIN_CTAS = 4;
-
-template <bool FUSED>
-__global__ void __launch_bounds__(TRACK_THREADS, TRACK_MIN_CTAS)
-nn_track_kernel(IcpWorkspace w, int write_d2) {
-    const int pair = blockIdx.y;
-    __shared__ double T[12], D[12], shift[3];
-    __shared__ int s_n, s_done;
-    __shared__ __align__(16) double scratch[TRACK_THREADS / 32][8 * 33];      // moment reduction scratch (two passes of 8)
-    if (threadIdx.x == 0) {
-        s_n = w.state[pair].n_src;
-        s_done = w.state[pair].done;
-    }
-    if (threadIdx.x < 12) {
-        T[threadIdx.x] = w.state[pair].T[threadIdx.x];
-        D[threadIdx.x] = w.state[pair].T[threadIdx.x] - w.state[pair].Tp[threadIdx.x];
-    }
-    if (threadIdx.x < 3) shift[threadIdx.x] = w.grid.params[pair].shift[threadIdx.x];
-    __syncthreads();
-    if (s_done) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Point4* pts = w.grid.sorted + (size_t)pair * w.grid.max_dst;
-    const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
-    int4* nbr = w.nbr + (size_t)pair * w.max_src;
-    float* budget = w.budget + (size_t)pair * w.max_src;
-    double* d2_out = w.d2 + (size_t)pair * w.max_src;
-    uint32_t* mask_out = w.srch_mask + (size_t)pair * w.task_cap;
-    const int n_tasks = (s_n + 31) / 32;
-    const int nvw = vwarps_for(s_n);
-    int* vw_counter = w.vw_counter + 2 * pair;
-    while (true) {
-        int vw = 0;
-        if (lane == 0) vw = atomicAdd(vw_counter, 1);
-        vw = __shfl_sync(0xffffffffu, vw, 0) * w.shard_world + w.shard_rank;      // (1, 0 unless the queries are sharded over GPUs)
-        if (vw >= nvw) break;
-        double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
-        for (int task = vw; task < n_tasks; task += nvw) {
-            const int i = task * 32 + lane;
-            const bool active = i < s_n;
-            bool settled = false;
-            double m[16];
-#pragma unroll
-            for (int k = 0; k < 16; k++) m[k] = 0.0;
-            if (active) {
-                const Point4 a = load_point(src + i);
-                const int4 nb = nbr[i];
-                const float bound = budget[i];
-                const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
-                const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
-                const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-                Best seed;
-                seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
-                double bx = 0.0, by = 0.0, bz = 0.0;
-                eval_list(seed, bx, by, bz, pts, nb, qx, qy, qz);
-                const float left = __fsub_rd(bound, query_movement(D, a, qx, qy, qz));
-                settled = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
-                if (settled) {
-                    // the same four names, the nearest in front; what is left of the bound
-                    int4 out;
-                    out.x = seed.pos;
-                    out.y = (nb.x != seed.pos) ? nb.x : nb.y;
-                    out.z = (nb.x != seed.pos && nb.y != seed.pos) ? nb.y : nb.z;
-                    out.w = (nb.w != seed.pos) ? nb.w : nb.z;
-                    if (out.x != nb.x) nbr[i] = out;
-                    budget[i] = left;
-                    if (!FUSED || write_d2) d2_out[i] = seed.d2;
-                    if (FUSED)
-                        accumulate_pair(m, qx - shift[0], qy - shift[1], qz - shift[2], bx - shift[0], by - shift[1], bz - shift[2],
-                                        sqrt(seed.d2));
-                }
-            }
-            const unsigned unsettled = __ballot_sync(0xffffffffu, active && !settled);
-            if (lane == 0) mask_out[task] = unsettled;
-            if (FUSED) acc += warp_reduce16_small(m, scratch[warp]);
-        }
-        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
-    }
-}
-
-// One CTA per pair: srch_off[t] = number of unsettled queries in tasks [0, t), srch_off[n_tasks] = their total.
-__global__ void __launch_bounds__(1024)
-srch_scan_kernel(IcpWorkspace w) {
-    const int pair = blockIdx.x;
-    if (w.state[pair].done) return;
-    const int n_tasks = (w.state[pair].n_src + 31) / 32;
-    const uint32_t* mask = w.srch_mask + (size_t)pair * w.task_cap;
-    uint32_t* off = w.srch_off + (size_t)pair * ((size_t)w.task_cap + 1);
-    __shared__ uint32_t warp_tot[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int start = 0; start < n_tasks; start += 1024) {
-        const int t = start + threadIdx.x;
-        const uint32_t v = (t < n_tasks) ? (uint32_t)__popc(mask[t]) : 0u;
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_tot[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t tt = warp_tot[lane];
-            uint32_t ts = tt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, ts, o);
-                if (lane >= o) ts += y;
-            }
-            warp_tot[lane] = ts - tt;
-        }
-        __syncthreads();
-        const uint32_t excl = carry + warp_tot[warp] + x - v;
-        if (t < n_tasks) off[t] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = excl + v;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) off[n_tasks] = carry;
-}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 template <int IMPL> struct SearchSmem;
 template <> struct SearchSmem<1> { double2 list[LEAN_WARP_SMEM]; };      // survivors list; never shared with the reduction: its stale slots must stay real points
 template <> struct SearchSmem<2> { TileWarp tile; };
 
-// QUEUED = false: the queue is the whole cloud and there are no neighbour lists yet (first iteration, nearest_neighbor());
-// QUEUED = true: the queue of the track kernel; the lanes recompute their query and the nearest listed point (the seed).
-// IMPL selects the search: 2 = tile_search.cuh (default), 1 = lean_search.cuh (round 1's warp-union walk, the
-// cross-check).  Both are exact, so every output bit is the same under either.
-template <int IMPL, bool QUEUED, bool FUSED>
+template <int IMPL, bool SEEDED, bool FUSED>
 __global__ void __launch_bounds__(NN_THREADS, IMPL == 2 ? R3D_TILE_MIN_CTAS : R3D_LEAN_MIN_CTAS)
 nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
     __shared__ double T[12], D[12];
-    __shared__ int s_n, s_done, s_nq;
+    __shared__ int s_n, s_done;
     // the grid's base pointers live in shared memory: the compiler would otherwise recompute these 64-bit
     // addresses inside every loop of the search
     __shared__ GridView s_view;
@@ -491,7 +325,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
         s_view = grid_view(w.grid, pair);
-        s_nq = QUEUED ? (int)w.srch_off[(size_t)pair * ((size_t)w.task_cap + 1) + (size_t)((w.state[pair].n_src + 31) / 32)] : w.state[pair].n_src;
     }
     if (threadIdx.x < 12) {
         T[threadIdx.x] = w.state[pair].T[threadIdx.x];
@@ -502,17 +335,14 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const GridView& v = s_view;
     const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
-    int4* nbr = w.nbr + (size_t)pair * w.max_src;
+    int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
     float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
-    const uint32_t* q_mask = w.srch_mask + (size_t)pair * w.task_cap;
-    const uint32_t* q_off = w.srch_off + (size_t)pair * ((size_t)w.task_cap + 1);
-    const int n_tasks32 = (s_n + 31) / 32;
     const int qpt = queries_per_task(s_n);
-    const int n_tasks = (s_nq + qpt - 1) / qpt;
+    const int n_tasks = (s_n + qpt - 1) / qpt;
     const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
-    int* vw_counter = w.vw_counter + 2 * pair + 1;
+    int* vw_counter = w.vw_counter + pair;
     unsigned phase = 0;      // parity of the warp's staging mbarrier(s)
     if constexpr (IMPL == 1) {
         list_init(ssm[warp].list, v.pts);
@@ -536,34 +366,52 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
         for (int task = vw; task < n_tasks; task += nvw) {
-            const int slot = task * qpt + (lane & (qpt - 1));      // qpt < 32: 32 / qpt lanes per query (replicas)
-            const bool active = slot < s_nq;
-            const bool primary = lane < qpt;                       // the replica that writes the results
-            int i = slot;
-            if (QUEUED && active) {
-                // queue entry `slot` -> sorted query: the task of 32 whose prefix count covers it, then the (r+1)-th set lane
-                int lo = 0, hi = n_tasks32 - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (__ldg(q_off + mid) <= (uint32_t)slot) lo = mid; else hi = mid - 1;
+            const int i = task * qpt + (lane & (qpt - 1));      // qpt < 32: 32 / qpt lanes per query (replicas)
+            const bool active = i < s_n;
+            const bool primary = lane < qpt;                    // the replica that writes the results
+#if R3D_NN_PREFETCH
+            // The virtual warp's next task is 2048 tasks away: nothing of it is in cache.  Once most lanes skip their
+            // search a task is a chain of dependent loads (query, previous neighbour's position, that point), so ask
+            // for the next task's lines now and for its neighbour points at the end of this task.
+            int pos_next = -1;
+            {
+                const int in = (task + nvw) * qpt + (lane & (qpt - 1));
+                if (task + nvw < n_tasks && in < s_n) {
+                    prefetch_l2(src + in);
+                    if (SEEDED) {
+                        pos_next = nn_pos[in];
+                        prefetch_l2(budget + in);
+                    }
                 }
-                i = lo * 32 + (int)__fns(__ldg(q_mask + lo), 0u, slot - (int)__ldg(q_off + lo) + 1);
             }
+#endif
             double qx = 0.0, qy = 0.0, qz = 0.0;
             Best seed, other;
             seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
             other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
             double sbx = 0.0, sby = 0.0, sbz = 0.0;      // coordinates of the seed
-            float slack = 0.0f;
+            float left = 0.0f, slack = 0.0f;      // bound on the other points left after this iteration's movement
+            bool skip = false;
             if (active) {
                 const Point4 a = load_point(src + i);
                 qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
                 qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
                 qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-                if (QUEUED) {
-                    eval_list(seed, sbx, sby, sbz, v.pts, nbr[i], qx, qy, qz);
-                    const float want = query_movement(D, a, qx, qy, qz) * tune.slack_mult;
-                    slack = ((want <= slack_max) ? want : 0.0f) + tune.slack_floor_frac * (float)g.cell;
+                if (SEEDED) {
+                    // (the tile kernel has registers to keep the seed's coordinates for the moment sums; the lean one, at 64, reloads)
+                    if constexpr (IMPL == 2) consider_xyz(seed, sbx, sby, sbz, v.pts, nn_pos[i], qx, qy, qz);
+                    else consider(seed, v.pts, nn_pos[i], qx, qy, qz);
+                    const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
+                    const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
+                    const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
+                    // rounded up; the last term covers the fp64 rounding of the two transformed positions themselves
+                    // (a few ulps of the coordinates), which matters only when coordinates are ~1e9 times the distances
+                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
+                                        __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
+                    left = __fsub_rd(budget[i], moved);
+                    skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
+                    const float want = moved * tune.slack_mult;
+                    slack = (want <= slack_max) ? want + 1e-4f * slack_max : 0.0f;
                 }
             }
             R3D_STAT(0, 1);
@@ -571,57 +419,47 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             const long long t_task = clock64();
 #endif
             float cover = 0.0f, lb_other = 0.0f;
-            TileList tl;
-            tl.p1 = tl.p2 = tl.p3 = -1;
-            tl.lb_rest = 0.0f;
             if constexpr (IMPL == 1) {
-                lean_search(ssm[warp].list, phase, seed, other, v, g, active, qx, qy, qz, slack, cover, qpt);
+                lean_search(ssm[warp].list, phase, seed, other, v, g, active && !skip, qx, qy, qz, slack, cover, qpt);
                 lb_other = sqrtf(__double2float_rd(other.d2));
             } else {
                 // (the range queue shares the warp's reduction scratch: the two are never live at the same time)
                 static_assert(sizeof(scratch[0]) >= TILE_QUEUE_WORDS * sizeof(uint32_t), "the range queue lives in the reduction scratch");
-                tile_search(ssm[warp].tile, reinterpret_cast<uint32_t*>(scratch[warp]), phase, seed, other, lb_other, tl, v, g, active,
+                tile_search(ssm[warp].tile, reinterpret_cast<uint32_t*>(scratch[warp]), phase, seed, other, lb_other, v, g, active && !skip,
                             qx, qy, qz, slack, cover, qpt);
             }
-            const bool seed_wins = !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
+            const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
 #ifdef R3D_NN_STATS
+            R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip && primary)));
+            // a skipped lane of the lean search still evaluates the warp's candidates: none of them may beat its seed
+            R3D_STAT(7, __popc(__ballot_sync(0xffffffffu, active && skip && (other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx)))));
             R3D_STAT(12, clock64() - t_task);
             R3D_STAT_MAX(13, clock64() - t_task);
 #endif
             const Best best = seed_wins ? seed : other;
             if (active && primary) {
+                nn_pos[i] = best.pos;
                 if (!FUSED || write_d2) d2_out[i] = best.d2;
-                // The list for the next iterations: the neighbour first, then the other points that are known by name.
-                // Everything that is NOT listed must be farther than `bound` (0 = no claim: search again next time).
-                int4 out = make_int4(best.pos, best.pos, best.pos, best.pos);
-                float bound = 0.0f;
-                const bool named = seed_wins || best.pos == tl.p1 || best.pos == tl.p2 || best.pos == tl.p3;
-                if (tl.lb_rest > 0.0f && named) {
-                    // the points a tile search ranked (its seed and p1..p3): every other point is beyond tl.lb_rest
-                    int n = 0;
-                    auto take = [&](int c) {
-                        if (c >= 0 && c != best.pos && n < 3) {
-                            if (n == 0) out.y = c; else if (n == 1) out.z = c; else out.w = c;
-                            n++;
-                        }
-                    };
-                    take(seed.pos); take(tl.p1); take(tl.p2); take(tl.p3);
-                    bound = tl.lb_rest * 0.999999f;
-                } else if (QUEUED && seed_wins) {
-                    // one neighbour known by name: every other point is beyond the nearest of the evaluated ones or the
-                    // radius the search covered (float square roots: the 1e-6 factors cover their rounding)
-                    bound = fminf(lb_other, cover) * 0.999999f;
+                float nb = 0.0f;
+                if (skip) {
+                    nb = left;
+                } else if (SEEDED && seed_wins) {
+                    // lower bound of the distance to any point other than the seed: the nearest of the evaluated ones or
+                    // the radius the search covered (float square roots: the 1e-6 factors cover their rounding)
+                    nb = fminf(lb_other, cover) * 0.999999f;
                 }
-                nbr[i] = out;
-                budget[i] = bound;
+                budget[i] = nb;
             }
+#if R3D_NN_PREFETCH
+            if (SEEDED && pos_next >= 0) prefetch_l2(v.pts + pos_next);
+#endif
             if (FUSED) {
                 double m[16];
 #pragma unroll
                 for (int k = 0; k < 16; k++) m[k] = 0.0;
                 if (active && primary) {
-                    double bx = sbx, by = sby, bz = sbz;      // (the seed's coordinates are still in registers)
-                    if (!seed_wins) {
+                    double bx = sbx, by = sby, bz = sbz;
+                    if (IMPL != 2 || !seed_wins) {
                         const Point4 b = load_point(v.pts + best.pos);
                         bx = b.x; by = b.y; bz = b.z;
                     }
@@ -631,7 +469,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 acc += warp_reduce16_small(m, scratch[warp]);
             }
         }
-        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)(nvw + vw)) * 16 + lane] = acc;
+        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
     }
 }
 
@@ -857,7 +695,7 @@ moments_kernel(IcpWorkspace w) {
     if (i < s.n_src) {
         // the three streams indexed by i are requested together (one memory latency instead of two before the gather)
         const double d2 = w.d2[(size_t)pair * w.max_src + i];
-        const int pos = w.nbr[(size_t)pair * w.max_src + i].x;
+        const int pos = w.nn_pos[(size_t)pair * w.max_src + i];
         const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
         if (kept(d2, i, s.tau, s.idx_cut)) {
             const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
@@ -902,13 +740,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     const int pair = blockIdx.x;
     PairState* st = w.state + pair;
-    if (threadIdx.x == 0) { w.vw_counter[2 * pair] = 0; w.vw_counter[2 * pair + 1] = 0; }      // this iteration's query launches have finished
+    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
     if (st->done) return;
     __shared__ double sm[SOLVE_THREADS];
     __shared__ double m[16];
     const int n = st->n_src;
     // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? 2 * vwarps_for(n) : (n + 31) / 32;
+    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32;
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -1026,7 +864,7 @@ export_kernel(IcpWorkspace w, const int32_t* __restrict__ src_off, int32_t* __re
     const size_t o = (size_t)src_off[pair] + a.idx;
     const double d2 = w.d2[(size_t)pair * w.max_src + i];
     if (out_idx) {
-        const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + w.nbr[(size_t)pair * w.max_src + i].x);
+        const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + w.nn_pos[(size_t)pair * w.max_src + i]);
         out_idx[o] = b.idx;
     }
     if (out_dist) out_dist[o] = sqrt_dist ? sqrt(d2) : d2;
@@ -1064,18 +902,17 @@ struct NnTimer {
 };
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
-static std::atomic<int> g_nn_impl{2};      // 2 = tile search (tile_search.cuh), 1 = warp-union walk (lean_search.cuh)
+static std::atomic<int> g_nn_impl{1};      // 1 = warp-union walk (lean_search.cuh), 2 = tile search (tile_search.cuh)
 static std::atomic<int> g_force_unfused{0}; // test knob: run partial_set_size == 1 through the select + moments kernels
 
-static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f}, g_slack_floor_frac{0.25e-4f};
+static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f};
 
 template <int IMPL>
-static int launch_query(IcpWorkspace& w, dim3 grid, bool queued, bool fused, int write_d2, cudaStream_t st) {
+static int launch_query(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
     LeanTuning tune;
     tune.slack_mult = g_slack_mult.load();
     tune.slack_max_frac = g_slack_max_frac.load();
-    tune.slack_floor_frac = g_slack_floor_frac.load();
-    if (queued) {
+    if (seeded) {
         if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
         else R3D_LAUNCH((nn_query_kernel<IMPL, true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
     } else {
@@ -1085,27 +922,21 @@ static int launch_query(IcpWorkspace& w, dim3 grid, bool queued, bool fused, int
     return R3D_OK;
 }
 
-// Persistent kernels: as many CTAs as are RESIDENT at once (148 SMs x the occupancy the kernel is compiled for)
+// Persistent query kernel: as many CTAs as are RESIDENT at once (148 SMs x the occupancy the kernel is compiled for)
 // spread over the chunk's pairs -- a CTA that has to wait for a slot would leave its pair without workers while the
-// others run -- and never more than one warp per task.
-static int ctas_per_pair(const IcpWorkspace& w, int resident_per_sm, int threads, int queries_per_task_) {
-    int per_pair = (148 * resident_per_sm) / w.n_pairs;
-    const int per_cta = queries_per_task_ * (threads / 32);
+// others run -- and never more than one warp per task (32 queries; 4 for small pairs).
+static int query_ctas_per_pair(const IcpWorkspace& w, int impl) {
+    int per_pair = (148 * (impl == 1 ? R3D_LEAN_MIN_CTAS : R3D_TILE_MIN_CTAS)) / w.n_pairs;
+    const int per_cta = queries_per_task(w.max_src) * (NN_THREADS / 32);
     const int cap = (w.max_src + per_cta - 1) / per_cta;
     if (per_pair > cap) per_pair = cap;
-    if (per_pair > vwarps_for(w.max_src) / (threads / 32)) per_pair = vwarps_for(w.max_src) / (threads / 32);
+    if (per_pair > vwarps_for(w.max_src) / (NN_THREADS / 32)) per_pair = vwarps_for(w.max_src) / (NN_THREADS / 32);
     return per_pair < 1 ? 1 : per_pair;
 }
 
-// The correspondence step of one iteration (see the comment above nn_track_kernel).  seeded = false: first iteration.
 static int launch_nn(IcpWorkspace& w, bool seeded, bool fused, int write_d2, cudaStream_t st) {
     const int impl = g_nn_impl.load();
-    if (seeded) {
-        R3D_LAUNCH((fused ? nn_track_kernel<true> : nn_track_kernel<false>), dim3(ctas_per_pair(w, TRACK_MIN_CTAS, TRACK_THREADS, 32), w.n_pairs),
-                   TRACK_THREADS, 0, st, w, write_d2);
-        R3D_LAUNCH(srch_scan_kernel, w.n_pairs, 1024, 0, st, w);
-    }
-    const dim3 grid(ctas_per_pair(w, impl == 1 ? R3D_LEAN_MIN_CTAS : R3D_TILE_MIN_CTAS, NN_THREADS, queries_per_task(w.max_src)), w.n_pairs);
+    const dim3 grid(query_ctas_per_pair(w, impl), w.n_pairs);
     if (impl == 1) return launch_query<1>(w, grid, seeded, fused, write_d2, st);
     return launch_query<2>(w, grid, seeded, fused, write_d2, st);
 }
@@ -1139,7 +970,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
         w.shard_rank = shard->rank;
         w.shard_world = shard->world;
     }
-    const size_t shard_doubles = (size_t)2 * vwarps_for(w.max_src) * 16;      // one pair (checked by the caller): track rows + search rows
+    const size_t shard_doubles = (size_t)vwarps_for(w.max_src) * 16;      // one pair (checked by the caller): rows [0, nvw)
     int rc = grid_build(w.grid, dst, dst_off, prm.cell_size, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(state_init_kernel, (P + 127) / 128, 128, 0, st, w, src_off, init_pose, prm.partial_set_size);
@@ -1149,8 +980,6 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
     R3D_LAUNCH(src_moments_kernel, qgrid, NN_THREADS, 0, st, w);
     R3D_LAUNCH(src_moments_reduce_kernel, P, SOLVE_THREADS, 0, st, w);
     const bool fused = prm.partial_set_size >= 1.0 && !g_force_unfused.load();
-    // (the first iteration has no track launch: its rows of the moment table must read as zero)
-    if (fused) R3D_CUDA(cudaMemsetAsync(w.partial, 0, (size_t)P * w.src_rows * 16 * sizeof(double), st));
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
     if (!fused) R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * SEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
     for (int it = 0; it < prm.max_iterations; it++) {
@@ -1335,10 +1164,6 @@ extern "C" int r3d_set_option(int option, double value) {
         case R3D_OPT_SLACK_MAX_FRAC:
             if (!(value >= 0.0 && value <= 64.0)) return R3D_ERR_INVALID;
             g_slack_max_frac.store((float)value);
-            return R3D_OK;
-        case R3D_OPT_SLACK_FLOOR_FRAC:
-            if (!(value >= 0.0 && value <= 64.0)) return R3D_ERR_INVALID;
-            g_slack_floor_frac.store((float)value);
             return R3D_OK;
         case R3D_OPT_CELL_FACTOR:
             if (!(value > 0.05 && value < 100.0)) return R3D_ERR_INVALID;

@@ -22,18 +22,20 @@
 //      sat in different blocks and rows at any time and the candidate loop ran at 7 % lane utilisation
 //      (profiles/r02_nn_tile_steps.md);
 //   3. filter = fp32, decision = fp64.  With block-relative coordinates the fp32 distance is off by at most
-//      `marg` (a few 1e-7 of the block size).  The walk keeps the FOUR smallest fp32 distances and the
-//      positions of the first three.  Afterwards the nearest candidate -- if its fp32 distance is within the
-//      lane's exact bound + marg -- is re-evaluated in fp64 from the original record, by all lanes at once,
-//      and only that value is compared and stored; the second and third follow while they, too, fall inside
-//      the error band of the new bound.  If even the fourth does (exact ties, duplicates, lattices) the round
-//      is repeated with an fp64 re-evaluation of every candidate in the band.  Everything else is provably
-//      farther than the best, so the result is the fp64 brute-force answer bit for bit;
-//   4. neighbour lists.  The three runners-up (with the seed, four points) and the fp32 distance of the
-//      FIFTH nearest, rounded inward, go back to the caller: every other point of the cloud is at least that
-//      far away, so while the query has moved by less than the gap the nearest neighbour is one of the four
-//      -- whichever it is now -- and the next iterations need no search at all (the query kernel keeps the
-//      list per query: the skip test of round 1 generalised from one neighbour to four).
+//      `marg` (a few 1e-7 of the block size).  The walk keeps the fp32 minimum and runner-up; afterwards the
+//      nearest candidate -- if its fp32 distance is within the lane's exact bound + marg -- is re-evaluated
+//      in fp64 from the original record, by all lanes at once, and only that value is compared and stored.
+//      When the runner-up also falls inside the error band (exact ties, duplicates, lattices) the queue is
+//      walked again with an fp64 re-evaluation of every candidate in the band.  Everything else is provably
+//      farther than the current best, so the result is the fp64 brute-force answer bit for bit.  The fp32
+//      minimum over the non-seed candidates, rounded inward, is the lower bound the caller's skip budget
+//      needs (it never needed more than a bound).
+//
+// Status (round 2): exact on every test, 14 candidate evaluations per query instead of 80, TMA-staged -- and
+// 1.3-2x SLOWER than the warp-union walk on the bench workload, so it is the opt-in search (R3D_OPT_NN_IMPL = 2).
+// The per-round machinery (union box, block lookups, staging, range building: ~1500 warp instructions) costs
+// what the cheaper evaluations save, and at 96 registers + 8.6 KB of staging per warp only 20 warps are
+// resident per SM.  Measurements and the variants that were tried: profiles/r02_nn_tile_search.md.
 #pragma once
 #include "lean_search.cuh"
 
@@ -97,22 +99,15 @@ __device__ __forceinline__ bool tile_exact(Best& other, const Point4* __restrict
 // (divide by 32 for the per-lane figure the lean search reports), 5 = block slots looked up, 6 = blocks staged,
 // 4 = staging passes, 14 = fp64 re-evaluations (lanes), 15 = records staged.
 
-struct TileList {          // what a tile search learned beyond the nearest neighbour (lanes that finished in a tile round)
-    int p1, p2, p3;        // sorted positions of the three nearest evaluated points other than the seed (fp32 ranking; -1 = none)
-    float lb_rest;         // every point other than the seed, p1, p2, p3 is at least this far from the query (0 = no claim)
-};
-
 // Arguments as lean_search; `lb_other` (out) = lower bound of the distance from the query to every evaluated
-// point other than the seed (+inf if there was none); `list` (out): see TileList; `queue`: TILE_QUEUE_WORDS words
-// of shared memory owned by the warp (may be reused by the caller between calls).
+// point other than the seed (+inf if there was none); `queue`: TILE_QUEUE_WORDS words of shared memory owned by
+// the warp (may be reused by the caller between calls).
 __device__ __forceinline__ void tile_search(TileWarp& S, uint32_t* queue, unsigned& phase, const Best& seed, Best& other, float& lb_other,
-                                            TileList& list, const GridView& v, const GridParams& g, bool active, double qx, double qy,
-                                            double qz, float slack, float& cover, int qpt = 32) {
+                                            const GridView& v, const GridParams& g, bool active, double qx, double qy, double qz,
+                                            float slack, float& cover, int qpt = 32) {
     const float inf = __int_as_float(0x7f800000);
     cover = 0.0f;
     lb_other = inf;
-    list.p1 = list.p2 = list.p3 = -1;
-    list.lb_rest = 0.0f;
     if (__ballot_sync(FULL, active) == 0u) return;      // (every lane of the task skips its search: the common case late in ICP)
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
@@ -130,7 +125,8 @@ __device__ __forceinline__ void tile_search(TileWarp& S, uint32_t* queue, unsign
     const uint32_t mbar = smem_u32(&S.mbar), pts_addr = smem_u32(S.pts), tbl_addr = smem_u32(S.tbl);
     float rcap = (seed.d2 < CUDART_INF) ? inf : R3D_LEAN_RCAP0 * (float)g.cell;
     bool fin = !active;
-    float o_t1 = inf, o_marg = 0.0f;      // of the lane's last round: nearest non-seed fp32 squared distance, error bound
+    float m2 = inf;            // fp32 minimum of the squared distances of the evaluated non-seed points
+    float margmax = 0.0f;      // largest error bound of the rounds this lane took part in
     while (true) {
         const unsigned unfin = __ballot_sync(FULL, !fin);
         if (unfin == 0u) break;
@@ -174,193 +170,162 @@ __device__ __forceinline__ void tile_search(TileWarp& S, uint32_t* queue, unsign
             const float marg = fmaf(4e-7f, fabsf(qux) + fabsf(quy) + fabsf(quz) + 2.0f * boff_max + 4.0f * cellf, eps_o);
             const int nslots = (int)nblk;
             const float inv_nbx = __fdividef(1.0f, (float)nbx), inv_nby = __fdividef(1.0f, (float)nby);      // (the quotients below are fixed up)
-            // the four smallest fp32 squared distances among this round's candidates (the seed excepted) and the sorted
-            // positions of the first three
-            float t1 = inf, t2 = inf, t3 = inf, t4 = inf;
-            int p1 = -1, p2 = -1, p3 = -1;
-            bool redo = false;      // this lane needs the exact walk (mode 1)
+            int dealt = 0;      // ranges met so far (replicas of a query share them out)
 #ifdef R3D_NN_STATS
             unsigned n_eval = 0, n_exact = 0;
 #endif
             R3D_STAT(5, nslots);
-            // mode 0: fp32 walk.  mode 1 (only if some lane found four or more candidates inside the error band of its
-            // bound): the same staging once more, the lanes concerned re-evaluating every candidate of the band in fp64.
-            for (int mode = 0; mode < 2; mode++) {
-                if (mode == 1 && !__any_sync(FULL, redo)) break;
-                const bool walker = part && (mode == 0 || redo);
-                float thr = tile_threshold(fmin(seed.d2, other.d2), marg);      // (mode 1)
-                int dealt = 0;      // ranges met so far (replicas of a query share them out)
-                int nq = 0;         // ranges in the lane's queue
-                // Phase B: the lane's queued ranges, one candidate per trip whatever range it belongs to.
-                auto consume = [&]() {
-                    int qi = 0, rel = 0;
-                    uint32_t k = 0, e = 0, seed_k = 0xffffffffu;
-                    float qrx = 0.0f, qry = 0.0f, qrz = 0.0f;
-                    while (true) {
-                        if (k == e) {
-                            if (qi == nq) break;
-                            const uint32_t u = queue[qi * 32 + lane];
-                            qi++;
-                            k = u & 0x1ffu;
-                            e = k + ((u >> 9) & 0x1ffu);
-                            const float4 bo = S.boff[u >> 18];
-                            qrx = qux - bo.x; qry = quy - bo.y; qrz = quz - bo.z;
-                            rel = __float_as_int(bo.w);
-                            seed_k = (uint32_t)(seed.pos + rel);      // where the seed sits if this range holds it
-                        }
-                        const float4 p = S.pts[k];
-                        const float dx = qrx - p.x, dy = qry - p.y, dz = qrz - p.z;
-                        const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        float x = (k == seed_k) ? inf : d2;
-                        if (mode == 0) {
-                            // insert (x, position) into the sorted four; earlier candidates stay ahead on equal distances
-                            int xp = (int)k - rel;
-                            bool c = x < t1;
-                            float lo = fminf(x, t1), hi = fmaxf(x, t1);
-                            int lop = c ? xp : p1, hip = c ? p1 : xp;
-                            t1 = lo; p1 = lop; x = hi; xp = hip;
-                            c = x < t2;
-                            lo = fminf(x, t2); hi = fmaxf(x, t2);
-                            lop = c ? xp : p2; hip = c ? p2 : xp;
-                            t2 = lo; p2 = lop; x = hi; xp = hip;
-                            c = x < t3;
-                            lo = fminf(x, t3); hi = fmaxf(x, t3);
-                            lop = c ? xp : p3;
-                            t3 = lo; p3 = lop;
-                            t4 = fminf(t4, hi);
-#ifdef R3D_NN_STATS
-                            n_eval++;
-#endif
-                        } else if (x <= thr) {
-#ifdef R3D_NN_STATS
-                            n_exact++;
-#endif
-                            if (tile_exact(other, v.pts, (int)k - rel, qx, qy, qz)) thr = tile_threshold(fmin(seed.d2, other.d2), marg);
-                        }
-                        k++;
-                    }
-                    nq = 0;
-                };
-                for (int base = 0; base < nslots; base += 32) {
-                    // ---- one block slot per lane
-                    const int sidx = base + lane;
-                    uint32_t cur = 0, end = 0, blk_id = 0;
-                    int cx4 = 0, cy4 = 0, cz4 = 0;
-                    if (sidx < nslots) {
-                        // sidx = (k2 * nby + k1) * nbx + k0: quotient by reciprocal, then fix up (exact for these small integers)
-                        int row = (int)((float)sidx * inv_nbx);
-                        row += (sidx - row * nbx >= nbx) - (sidx - row * nbx < 0);
-                        const int k0 = sidx - row * nbx;
-                        int k2 = (int)((float)row * inv_nby);
-                        k2 += (row - k2 * nby >= nby) - (row - k2 * nby < 0);
-                        const int k1 = row - k2 * nby;
-                        const int cbx = ubx0 + k0, cby = uby0 + k1, cbz = ubz0 + k2;
-                        const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
-                        const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
-                        if (b >= 0) {
-                            cx4 = cbx * 4; cy4 = cby * 4; cz4 = cbz * 4;
-                            // cells of the block inside the union box lie between its first and last such cell (z, y, x order)
-                            const int x0 = max(lox, cx4) - cx4, x1 = min(hix, cx4 + 3) - cx4;
-                            const int y0 = max(loy, cy4) - cy4, y1 = min(hiy, cy4 + 3) - cy4;
-                            const int z0 = max(loz, cz4) - cz4, z1 = min(hiz, cz4 + 3) - cz4;
-                            const uint32_t* cs = v.cell_start + (size_t)b * 64;
-                            cur = __ldg(cs + ((z0 << 4) | (y0 << 2) | x0));
-                            end = __ldg(cs + ((z1 << 4) | (y1 << 2) | x1) + 1);
-                            blk_id = (uint32_t)b;
-                        }
-                    }
-                    // ---- stage and walk; several passes when the slots do not fit at once
-                    while (true) {
-                        const uint32_t c = min(end - cur, (uint32_t)TILE_CAP);
-                        const unsigned hm = __ballot_sync(FULL, c > 0u);
-                        if (hm == 0u) break;
-                        uint32_t incl = c;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const uint32_t y = __shfl_up_sync(FULL, incl, o);
-                            if (lane >= o) incl += y;
-                        }
-                        const int rank = __popc(hm & lt);
-                        const bool fits = c > 0u && incl <= (uint32_t)TILE_CAP && rank < TILE_TBLS;      // a prefix of the occupied slots
-                        const unsigned fm = __ballot_sync(FULL, fits);
-                        const int nfit = __popc(fm);
-                        const uint32_t totpts = __shfl_sync(FULL, incl, 31 - __clz(fm));
-                        R3D_STAT(4, 1);
-                        R3D_STAT(6, nfit);
-                        R3D_STAT(15, totpts);
-                        if (lane == 0) mbar_arrive_expect_tx(mbar, totpts * 16u + (uint32_t)nfit * (TILE_TBL_WORDS * 4u));
-                        __syncwarp();
-                        if (fits) {
-                            const uint32_t excl = incl - c;
-                            bulk_copy_g2s(pts_addr + excl * 16u, v.packed + cur, c * 16u, mbar);
-                            bulk_copy_g2s(tbl_addr + (uint32_t)rank * (TILE_TBL_WORDS * 4u), v.cell_start + (size_t)blk_id * 64, TILE_TBL_WORDS * 4u, mbar);
-                            TileSlot sl;
-                            sl.win_lo = cur; sl.win_hi = cur + c; sl.rel = (int32_t)excl - (int32_t)cur; sl.pad = 0;
-                            sl.cx4 = cx4; sl.cy4 = cy4; sl.cz4 = cz4; sl.pad2 = 0;
-                            S.slot[rank] = sl;
-                            S.boff[rank] = make_float4((float)(cx4 - 4 * ubx0) * cellf, (float)(cy4 - 4 * uby0) * cellf,
-                                                       (float)(cz4 - 4 * ubz0) * cellf, __int_as_float(sl.rel));
-                        }
-                        __syncwarp();
-                        mbar_wait(mbar, phase & 1u);
-                        phase ^= 1u;
-                        if (walker) {
-                            // Phase A: one range per staged block and z-slab of the lane's box
-                            for (int r = 0; r < nfit; r++) {
-                                const TileSlot sl = S.slot[r];
-                                const int x0 = max(mlox, sl.cx4) - sl.cx4, x1 = min(mhix, sl.cx4 + 3) - sl.cx4;
-                                const int y0 = max(mloy, sl.cy4) - sl.cy4, y1 = min(mhiy, sl.cy4 + 3) - sl.cy4;
-                                const int z0 = max(mloz, sl.cz4) - sl.cz4, z1 = min(mhiz, sl.cz4 + 3) - sl.cz4;
-                                if (x0 > x1 || y0 > y1 || z0 > z1) continue;
-                                // gaps (cells) between the query and the part of the block that is looked at
-                                const float ux = tqx - (float)sl.cx4, uy = tqy - (float)sl.cy4, uz = tqz - (float)sl.cz4;
-                                const float gx = fmaxf(fmaxf(fmaxf((float)x0 - ux, ux - (float)(x1 + 1)), 0.0f) - mgx, 0.0f);
-                                const float gy = fmaxf(fmaxf(fmaxf((float)y0 - uy, uy - (float)(y1 + 1)), 0.0f) - mgy, 0.0f);
-                                const float gxy = fmaf(gy, gy, gx * gx);
-                                if (gxy > rc2) continue;
-                                const uint32_t* tb = S.tbl[r];
-                                for (int iz = z0; iz <= z1; iz++) {
-                                    const float gz = fmaxf(fmaxf(fmaxf((float)iz - uz, uz - (float)(iz + 1)), 0.0f) - mgz, 0.0f);
-                                    if (fmaf(gz, gz, gxy) > rc2) continue;
-                                    const uint32_t s = max(tb[(iz << 4) | (y0 << 2) | x0], sl.win_lo);
-                                    const uint32_t e = min(tb[((iz << 4) | (y1 << 2) | x1) + 1], sl.win_hi);
-                                    if (s >= e) continue;
-                                    if (nrep > 1) {      // the replicas of a query share its ranges out
-                                        const bool mine = (dealt & (nrep - 1)) == rep;
-                                        dealt++;
-                                        if (!mine) continue;
-                                    }
-                                    queue[nq * 32 + lane] = (uint32_t)((int)s + sl.rel) | ((e - s) << 9) | ((uint32_t)r << 18);
-                                    if (++nq == TILE_QCAP) consume();
-                                }
-                            }
-                            consume();
-                        }
-                        __syncwarp();      // every lane is done with the staged data: the next pass may overwrite it
-                        if (fits) cur += c;
+            for (int base = 0; base < nslots; base += 32) {
+                // ---- one block slot per lane
+                const int sidx = base + lane;
+                uint32_t cur = 0, end = 0, blk_id = 0;
+                int cx4 = 0, cy4 = 0, cz4 = 0;
+                if (sidx < nslots) {
+                    // sidx = (k2 * nby + k1) * nbx + k0: quotient by reciprocal, then fix up (exact for these small integers)
+                    int row = (int)((float)sidx * inv_nbx);
+                    row += (sidx - row * nbx >= nbx) - (sidx - row * nbx < 0);
+                    const int k0 = sidx - row * nbx;
+                    int k2 = (int)((float)row * inv_nby);
+                    k2 += (row - k2 * nby >= nby) - (row - k2 * nby < 0);
+                    const int k1 = row - k2 * nby;
+                    const int cbx = ubx0 + k0, cby = uby0 + k1, cbz = ubz0 + k2;
+                    const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
+                    const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
+                    if (b >= 0) {
+                        cx4 = cbx * 4; cy4 = cby * 4; cz4 = cbz * 4;
+                        // cells of the block inside the union box lie between its first and last such cell (z, y, x order)
+                        const int x0 = max(lox, cx4) - cx4, x1 = min(hix, cx4 + 3) - cx4;
+                        const int y0 = max(loy, cy4) - cy4, y1 = min(hiy, cy4 + 3) - cy4;
+                        const int z0 = max(loz, cz4) - cz4, z1 = min(hiz, cz4 + 3) - cz4;
+                        const uint32_t* cs = v.cell_start + (size_t)b * 64;
+                        cur = __ldg(cs + ((z0 << 4) | (y0 << 2) | x0));
+                        end = __ldg(cs + ((z1 << 4) | (y1 << 2) | x1) + 1);
+                        blk_id = (uint32_t)b;
                     }
                 }
-                if (mode == 0 && part) {
-                    // fp64 re-evaluation of the nearest candidates, by all lanes at once (a load inside the walk would stall
-                    // the whole warp once per lane that needs one).  Candidate n+1 matters only while it lies inside the error
-                    // band of the bound that the first n left behind.
-                    float band = tile_threshold(fmin(seed.d2, other.d2), marg);
-                    if (p1 >= 0 && t1 <= band) {
+                // ---- stage and walk; several passes when the slots do not fit at once
+                while (true) {
+                    const uint32_t c = min(end - cur, (uint32_t)TILE_CAP);
+                    const unsigned hm = __ballot_sync(FULL, c > 0u);
+                    if (hm == 0u) break;
+                    uint32_t incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += y;
+                    }
+                    const int rank = __popc(hm & lt);
+                    const bool fits = c > 0u && incl <= (uint32_t)TILE_CAP && rank < TILE_TBLS;      // a prefix of the occupied slots
+                    const unsigned fm = __ballot_sync(FULL, fits);
+                    const int nfit = __popc(fm);
+                    const uint32_t totpts = __shfl_sync(FULL, incl, 31 - __clz(fm));
+                    R3D_STAT(4, 1);
+                    R3D_STAT(6, nfit);
+                    R3D_STAT(15, totpts);
+                    if (lane == 0) mbar_arrive_expect_tx(mbar, totpts * 16u + (uint32_t)nfit * (TILE_TBL_WORDS * 4u));
+                    __syncwarp();
+                    if (fits) {
+                        const uint32_t excl = incl - c;
+                        bulk_copy_g2s(pts_addr + excl * 16u, v.packed + cur, c * 16u, mbar);
+                        bulk_copy_g2s(tbl_addr + (uint32_t)rank * (TILE_TBL_WORDS * 4u), v.cell_start + (size_t)blk_id * 64, TILE_TBL_WORDS * 4u, mbar);
+                        TileSlot sl;
+                        sl.win_lo = cur; sl.win_hi = cur + c; sl.rel = (int32_t)excl - (int32_t)cur; sl.pad = 0;
+                        sl.cx4 = cx4; sl.cy4 = cy4; sl.cz4 = cz4; sl.pad2 = 0;
+                        S.slot[rank] = sl;
+                        S.boff[rank] = make_float4((float)(cx4 - 4 * ubx0) * cellf, (float)(cy4 - 4 * uby0) * cellf,
+                                                   (float)(cz4 - 4 * ubz0) * cellf, __int_as_float(sl.rel));
+                    }
+                    __syncwarp();
+                    mbar_wait(mbar, phase & 1u);
+                    phase ^= 1u;
+                    if (part) {
+                        float m1 = inf, c2 = inf;      // nearest and second-nearest fp32 squared distance among the queued candidates
+                        int k1 = -1;                   // sorted position of the nearest
+                        int nq = 0;
+                        // Phase B: the lane's queued ranges.  exact = false: fp32 only, tracking (m1, k1, c2);
+                        // exact = true: every candidate within thr of the query, except k1, is re-evaluated in fp64.
+                        auto walk = [&](const bool exact, float thr) {
+                            for (int qi = 0; qi < nq; qi++) {
+                                const uint32_t u = queue[qi * 32 + lane];
+                                uint32_t k = u & 0x1ffu;
+                                const uint32_t e = k + ((u >> 9) & 0x1ffu);
+                                const float4 bo = S.boff[u >> 18];
+                                const float qrx = qux - bo.x, qry = quy - bo.y, qrz = quz - bo.z;
+                                const int rel = __float_as_int(bo.w);
+                                const uint32_t seed_k = (uint32_t)(seed.pos + rel);      // where the seed sits if this range holds it
+                                do {
+                                    const float4 p = S.pts[k];
+                                    const float dx = qrx - p.x, dy = qry - p.y, dz = qrz - p.z;
+                                    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                                    const float d2e = (k == seed_k) ? inf : d2;
+                                    if (!exact) {
+                                        c2 = fminf(c2, fmaxf(m1, d2e));
+                                        if (d2e < m1) { m1 = d2e; k1 = (int)k - rel; }
 #ifdef R3D_NN_STATS
-                        n_exact++;
+                                        n_eval++;
 #endif
-                        tile_exact(other, v.pts, p1, qx, qy, qz);
-                        band = tile_threshold(fmin(seed.d2, other.d2), marg);
-                        if (p2 >= 0 && t2 <= band) {
-                            tile_exact(other, v.pts, p2, qx, qy, qz);
-                            band = tile_threshold(fmin(seed.d2, other.d2), marg);
-                            if (p3 >= 0 && t3 <= band) {
-                                tile_exact(other, v.pts, p3, qx, qy, qz);
-                                band = tile_threshold(fmin(seed.d2, other.d2), marg);
-                                redo = t4 <= band;
+                                    } else if (d2e <= thr && (int)k - rel != k1) {
+#ifdef R3D_NN_STATS
+                                        n_exact++;
+#endif
+                                        if (tile_exact(other, v.pts, (int)k - rel, qx, qy, qz)) thr = tile_threshold(fmin(seed.d2, other.d2), marg);
+                                    }
+                                } while (++k < e);
+                            }
+                        };
+                        // The fp32 walk remembers the nearest candidate (m1 at k1) and the runner-up distance (c2).  k1 alone
+                        // is then re-evaluated in fp64 -- by all lanes at once: a load inside the walk would stall the whole
+                        // warp once per lane that needs one -- and unless the runner-up also lies within the error band of
+                        // the new bound, nothing else that was queued can be the neighbour.  Otherwise (exact or near ties:
+                        // duplicate points, lattices) the queue is walked again, re-evaluating every candidate in the band.
+                        auto flush = [&]() {
+                            if (nq > 0) {
+                                walk(false, 0.0f);
+                                m2 = fminf(m2, m1);
+                                if (k1 >= 0 && m1 <= tile_threshold(fmin(seed.d2, other.d2), marg)) {
+#ifdef R3D_NN_STATS
+                                    n_exact++;
+#endif
+                                    tile_exact(other, v.pts, k1, qx, qy, qz);
+                                    const float thr = tile_threshold(fmin(seed.d2, other.d2), marg);
+                                    if (c2 <= thr) walk(true, thr);
+                                }
+                            }
+                            m1 = inf; c2 = inf; k1 = -1; nq = 0;
+                        };
+                        // Phase A: one range per staged block and z-slab of the lane's box
+                        for (int r = 0; r < nfit; r++) {
+                            const TileSlot sl = S.slot[r];
+                            const int x0 = max(mlox, sl.cx4) - sl.cx4, x1 = min(mhix, sl.cx4 + 3) - sl.cx4;
+                            const int y0 = max(mloy, sl.cy4) - sl.cy4, y1 = min(mhiy, sl.cy4 + 3) - sl.cy4;
+                            const int z0 = max(mloz, sl.cz4) - sl.cz4, z1 = min(mhiz, sl.cz4 + 3) - sl.cz4;
+                            if (x0 > x1 || y0 > y1 || z0 > z1) continue;
+                            // gaps (cells) between the query and the part of the block that is looked at
+                            const float ux = tqx - (float)sl.cx4, uy = tqy - (float)sl.cy4, uz = tqz - (float)sl.cz4;
+                            const float gx = fmaxf(fmaxf(fmaxf((float)x0 - ux, ux - (float)(x1 + 1)), 0.0f) - mgx, 0.0f);
+                            const float gy = fmaxf(fmaxf(fmaxf((float)y0 - uy, uy - (float)(y1 + 1)), 0.0f) - mgy, 0.0f);
+                            const float gxy = fmaf(gy, gy, gx * gx);
+                            if (gxy > rc2) continue;
+                            const uint32_t* tb = S.tbl[r];
+                            for (int iz = z0; iz <= z1; iz++) {
+                                const float gz = fmaxf(fmaxf(fmaxf((float)iz - uz, uz - (float)(iz + 1)), 0.0f) - mgz, 0.0f);
+                                if (fmaf(gz, gz, gxy) > rc2) continue;
+                                const uint32_t s = max(tb[(iz << 4) | (y0 << 2) | x0], sl.win_lo);
+                                const uint32_t e = min(tb[((iz << 4) | (y1 << 2) | x1) + 1], sl.win_hi);
+                                if (s >= e) continue;
+                                if (nrep > 1) {      // the replicas of a query share its ranges out
+                                    const bool mine = (dealt & (nrep - 1)) == rep;
+                                    dealt++;
+                                    if (!mine) continue;
+                                }
+                                queue[nq * 32 + lane] = (uint32_t)((int)s + sl.rel) | ((e - s) << 9) | ((uint32_t)r << 18);
+                                if (++nq == TILE_QCAP) flush();
                             }
                         }
+                        flush();
                     }
+                    __syncwarp();      // every lane is done with the staged data: the next pass may overwrite it
+                    if (fits) cur += c;
                 }
             }
 #ifdef R3D_NN_STATS
@@ -369,26 +334,19 @@ __device__ __forceinline__ void tile_search(TileWarp& S, uint32_t* queue, unsign
 #endif
             if (nrep > 1) {
                 // the replicas of a query have each walked a share of its ranges: give all of them the minimum, so that they
-                // keep taking the same decisions (the lists of replicas are not merged: no list for such queries)
+                // keep taking the same decisions
                 for (int o = qpt; o < 32; o <<= 1) {
                     const double od2 = __shfl_xor_sync(FULL, other.d2, o);
                     const int oidx = __shfl_xor_sync(FULL, other.idx, o), opos = __shfl_xor_sync(FULL, other.pos, o);
                     if (od2 < other.d2 || (od2 == other.d2 && oidx < other.idx)) { other.d2 = od2; other.idx = oidx; other.pos = opos; }
-                    t1 = fminf(t1, __shfl_xor_sync(FULL, t1, o));
+                    m2 = fminf(m2, __shfl_xor_sync(FULL, m2, o));
                 }
             }
             if (part) {
-                o_t1 = t1;
-                o_marg = marg;
+                margmax = fmaxf(margmax, marg);
                 const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                 fin = own_whole || (rn <= ruse) || !(ruse < 1e37f);
-                if (fin) {
-                    cover = own_whole ? inf : ruse;
-                    if (nrep == 1) {
-                        list.p1 = p1; list.p2 = p2; list.p3 = p3;
-                        list.lb_rest = fminf(fmaxf(sqrtf(t4) * 0.999999f - marg, 0.0f), cover);
-                    }
-                }
+                if (fin) cover = own_whole ? inf : ruse;
                 rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the box) must not set the next radius
             }
         } else {
@@ -402,8 +360,7 @@ __device__ __forceinline__ void tile_search(TileWarp& S, uint32_t* queue, unsign
                 const Best found = far_query_search(owner, seed, v, g, qx, qy, qz, ruse, all_scanned);
                 if (lane % qpt == owner) {
                     if (found.d2 < other.d2 || (found.d2 == other.d2 && found.idx < other.idx)) other = found;
-                    o_t1 = __double2float_rd(found.d2);
-                    o_marg = 0.0f;
+                    m2 = fminf(m2, __double2float_rd(found.d2));
                     const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                     fin = all_scanned || (rn <= ruse) || !(ruse < 1e37f);
                     if (fin) cover = all_scanned ? inf : ruse;
@@ -412,7 +369,7 @@ __device__ __forceinline__ void tile_search(TileWarp& S, uint32_t* queue, unsign
             }
         }
     }
-    lb_other = fmaxf(sqrtf(o_t1) * 0.999999f - o_marg, 0.0f);
+    lb_other = fmaxf(sqrtf(m2) * 0.999999f - margmax, 0.0f);
 }
 
 }  // namespace r3d

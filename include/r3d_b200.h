@@ -265,19 +265,17 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tuning knobs; none of them changes results (process-wide, read when a call is issued).
- *   R3D_OPT_NN_IMPL        2 = tile search (default, csrc/tile_search.cuh: blocks staged by TMA, per-lane walk, fp32 filter +
- *                          fp64 decision), 1 = warp-union walk (csrc/lean_search.cuh, round 1's search, kept as cross-check)
+ *   R3D_OPT_NN_IMPL        1 = warp-union walk (default, csrc/lean_search.cuh), 2 = tile search (csrc/tile_search.cuh: blocks staged
+ *                          into shared memory by TMA, per-lane walk, fp32 filter + fp64 decision; exact too, slower on the bench
+ *                          workload -- profiles/r02_nn_tile_search.md)
  *   R3D_OPT_FORCE_UNFUSED  non-zero: partial_set_size == 1 also runs through the selection + moments kernels (test knob)
  *   R3D_OPT_CELL_FACTOR    automatic grid cell edge in units of the estimated point spacing (used when cell_size <= 0; default 2)
  *   R3D_OPT_SLACK_MULT, R3D_OPT_SLACK_MAX_FRAC
  *                          how much larger than its bound a seeded search ball is made: a multiple of the query's movement in
  *                          this iteration (default 8), used while that is at most a fraction of the cell edge (default 0.25);
- *                          a multiple of 0 disables the skipping of searches that cannot change the neighbour
- *   R3D_OPT_SLACK_FLOOR_FRAC
- *                          added to that radius, as a fraction of the cell edge: room for the neighbour LIST of the tile search
- *                          (the query's four nearest points; csrc/tile_search.cuh) to outlast several iterations */
+ *                          a multiple of 0 disables the skipping of searches that cannot change the neighbour */
 typedef enum {
-    R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5, R3D_OPT_FORCE_UNFUSED = 6, R3D_OPT_SLACK_FLOOR_FRAC = 7
+    R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5, R3D_OPT_FORCE_UNFUSED = 6
 } r3d_option;
 int r3d_set_option(int option, double value);
 

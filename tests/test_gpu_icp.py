@@ -176,17 +176,17 @@ def test_search_skipping_and_search_variants_do_not_change_results():
     try:
         base = run(25)
         Tb = base["T"].cpu().numpy()
-        # no skipping; generous slack; large cap; round 1's warp-union walk instead of the tile search.  Every variant
+        # no skipping; generous slack; large cap; the tile search instead of the warp-union walk.  Every variant
         # is an exact search feeding the same fixed-order sums, so every bit must agree.
-        for opt, val in ((4, 0.0), (4, 64.0), (5, 1.0), (3, 1.0)):
+        for opt, val in ((4, 0.0), (4, 64.0), (5, 1.0), (3, 2.0)):
             assert L.r3d_set_option(opt, val) == 0
             r = run(25)
             assert np.array_equal(r["T"].cpu().numpy(), Tb), (opt, val)
             assert np.array_equal(r["idx"].cpu().numpy(), base["idx"].cpu().numpy()), (opt, val)
             assert np.array_equal(r["dist"].cpu().numpy(), base["dist"].cpu().numpy()), (opt, val)
-            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 2.0)
+            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0)
     finally:
-        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 2.0)
+        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0)
     # the last iteration's correspondences against brute force: src of iteration 25 = T_24 * A, which is the
     # pose after 24 iterations
     T24 = run(24)["T"][0].cpu().numpy()

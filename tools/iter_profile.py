@@ -26,12 +26,10 @@ L = C.lib()
 a, b = bench.synth_batch_torch(pairs, 0, torch.device("cuda", 0))
 stats_on = L.r3d_nn_stats_read(None, 1) == 0
 prev_ms, prev = 0.0, [0] * 16
-impl = int(os.environ.get("IMPL", "2"))
+impl = int(os.environ.get("IMPL", "1"))
 L.r3d_set_option(3, float(impl))
-if os.environ.get("FLOOR"):
-    assert L.r3d_set_option(7, float(os.environ["FLOOR"])) == 0
 per_lane = 32.0 if impl == 2 else 1.0      # the tile search counts evaluations summed over the lanes
-print("iter  launch_us  rounds/task  search tasks / 1000 queries  candidates/lane  staged blocks/task  staged records/task  fp64 re-evals/query  mean_err")
+print("iter  launch_us  rounds/task  searching lanes/task  candidates/lane  staged blocks/task  staged records/task  fp64 re-evals/query  mean_err")
 for k in range(1, iters + 1):
     kw = dict(max_iterations=k, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)
     best = None
@@ -52,6 +50,6 @@ for k in range(1, iters + 1):
     d = [c - p for c, p in zip(cur, prev)]
     tasks = max(d[0], 1)
     print("%4d  %9.1f  %11.2f  %20.2f  %15.1f  %18.2f  %19.1f  %19.3f  %.6f" % (
-        k, 1e3 * (best - prev_ms), d[1] / tasks, 1000.0 * d[0] / float(out["n_src"].sum()), d[2] / tasks / per_lane, d[6] / tasks, d[15] / tasks,
+        k, 1e3 * (best - prev_ms), d[1] / tasks, 32 - d[3] / tasks, d[2] / tasks / per_lane, d[6] / tasks, d[15] / tasks,
         d[14] / tasks / 32.0, float(out["mean_err"][0])), flush=True)
     prev_ms, prev = best, cur

@@ -16,7 +16,7 @@ partial = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 group = int(sys.argv[4]) if len(sys.argv) > 4 else 32
 factor = float(sys.argv[5]) if len(sys.argv) > 5 else 2.0
-impl = int(sys.argv[6]) if len(sys.argv) > 6 else 2
+impl = int(sys.argv[6]) if len(sys.argv) > 6 else 1
 warm = int(os.environ.get("WARM", "1"))
 
 import bench  # noqa: E402
