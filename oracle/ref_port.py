@@ -11,9 +11,12 @@ Parity status: PINNED.  ``tests/golden/make_golden.py`` imports the unmodified
 reference from ``/root/reference`` (through a stub shim for matplotlib / skimage /
 open3d, which the arithmetic never touches), runs it on seeded inputs and stores
 inputs + outputs in ``tests/golden/*.npz``; ``tests/test_oracle_golden.py``
-checks every function below against those vectors.  One exception, flagged where
-it is defined: ``score_hypotheses_3d`` (K4B) has no reference implementation at
-all, so it is a composition of reference primitives and is "parity unpinned".
+checks every function below against those vectors.  ``score_hypotheses_3d`` (K4B)
+has no single reference function behind it: it is the composition of reference
+primitives SURVEY.md section 8(c) defines, and it is pinned by ``tests/golden/k4b.npz``,
+which ``tests/golden/make_golden_k4b.py`` produced by running that composition with the
+reference's OWN functions (``rigid_transform_3D``, ``homo_rigid_transform_3d``,
+``get_transformed_points``) imported from ``/root/reference``.
 
 Third-party arithmetic the reference delegates to (not vendored under
 ``/root/reference``): scikit-learn ``NearestNeighbors`` (pinned 0.20.3,
@@ -403,10 +406,49 @@ def ransac_loop(img1, img2, kp1, kp2, bf_matches, plot=False, x0=None, y0=None, 
 
 
 # --------------------------------------------------------------------------------------
-# K4B: 3-D hypothesis scoring.  NO REFERENCE IMPLEMENTATION EXISTS -- parity unpinned.
-# Composition of reference primitives: residual of
+# register_imgs (utils/transformation3d.py:217-289): the glue of BASELINE.json configs[0].
+# --------------------------------------------------------------------------------------
+
+def register_imgs(img1, img2, depth1, depth2, pts1, pts2, filter_pts_frac=1., partial_set_frac=1., run_icp=True, record=None):
+    """utils/transformation3d.py:240-289 out of the oracle's own pieces: SIFT + cross-checked brute-force matching
+    (OpenCV, the reference's third-party dependency, :27-32), ransac_loop (:243), rounded int16 keypoints and their
+    depths with zero-depth pairs dropped (:252-261), the affine fit (:267), the transformed cloud (:268), the two
+    np.random.choice sub-samples from the global RNG (:271-272), ICP (:275-278) and h.t (:289).
+    run_icp=False stops before ICP (which draws no random numbers) and returns h; `record` (a dict) receives the
+    intermediate results."""
+    import cv2
+    sift = cv2.xfeatures2d.SIFT_create() if hasattr(cv2, "xfeatures2d") else cv2.SIFT_create()
+    kp1, des1 = sift.detectAndCompute(img1, mask=None)
+    kp2, des2 = sift.detectAndCompute(img2, mask=None)
+    bf = cv2.BFMatcher(normType=cv2.NORM_L2, crossCheck=True).match(des1, des2)
+    bf = np.array([(m.queryIdx, m.trainIdx) for m in bf])
+    _, matches = ransac_loop(img1, img2, kp1, kp2, bf)
+    p1 = np.rint(np.array([kp1[m[0]].pt for m in matches])).astype(np.int16)
+    p2 = np.rint(np.array([kp2[m[1]].pt for m in matches])).astype(np.int16)
+    k1 = [(p[0], p[1], depth1[p[1], p[0]]) for p in p1]
+    k2 = [(p[0], p[1], depth2[p[1], p[0]]) for p in p2]
+    kept = [z for z in zip(k1, k2) if z[0][2] != 0 and z[1][2] != 0]
+    k1, k2 = (np.array(x) for x in zip(*kept))
+    h = homo_rigid_transform_3d(k1, k2)
+    moved = get_transformed_points(pts1, h)
+    i1 = np.random.choice(moved.shape[0], int(moved.shape[0] * filter_pts_frac), replace=False)
+    i2 = np.random.choice(pts2.shape[0], int(pts2.shape[0] * filter_pts_frac), replace=False)
+    if record is not None:
+        record.update(matches=np.array(matches), h=h, n_icp_src=len(i1))
+    if not run_icp:
+        return h
+    t, _, it = icp(moved[i1], pts2[i2], tolerance=0.001, max_iterations=100, partial_set_size=partial_set_frac)
+    if record is not None:
+        record.update(icp_iters=it, icp_T=t)
+    return np.dot(h, t)
+
+
+# --------------------------------------------------------------------------------------
+# K4B: 3-D hypothesis scoring (BASELINE.json configs[4]).  The reference has no single function for it;
+# SURVEY.md section 8(c) defines it as a composition of reference primitives: residual of
 # get_transformed_points (utils/transformation3d.py:183-187) against Q, inlier iff the
 # squared residual is below the reference's SSD threshold (q9.py:122), counted in fp64.
+# Pinned by tests/golden/k4b.npz: the same composition run with the reference's own functions.
 # --------------------------------------------------------------------------------------
 
 def score_hypotheses_3d(T, P, Q, thresh=10.0, chunk=64):

@@ -226,3 +226,95 @@ def test_register_consecutive_pairs_batches_the_icp_stage():
         assert np.array_equal(a, b)
     assert_transform_parity(bat[0], g["final_h"], O.scene_extent(clouds[0]), "first pair vs the reference run")
     assert rec.register_consecutive_pairs(clouds[:1], gray[:1], depth[:1]) == []
+
+
+def _digest(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], dtype=np.uint64)[0]
+
+
+def test_sofa_config0_all_seven_pairs():
+    """BASELINE.json configs[0] IN FULL: `reconstruct_rgbd.py --mode 3dhomo` on examples/sofa_rgbd -- the pair loop of
+    trans3d_proc (reconstruct.py:319-329) over all 8 frames with the reference's own settings (filter_pts_frac 0.1,
+    partial_set_frac 0.7, one seed before the loop).  tests/golden/make_golden_configs.py recorded the unmodified
+    reference's 7 returned 4x4s, RANSAC inlier lists (hashed), ICP iteration counts and the final state of the global
+    RNG; the drop-in register_consecutive_pairs must reproduce all of them."""
+    import time
+    import warnings
+    pytest.importorskip("cv2")
+    from conftest import load_golden
+    t3d = sub("utils.transformation3d")
+    ops = sub("ops")
+    rec = sub("reconstruct")
+    g = load_golden("sofa_config0")
+    gray, depth = list(g["gray"]), list(g["depth"])
+    clouds = rec.depth_images_to_3d_pts_ld(depth)
+    assert [c.shape[0] for c in clouds] == list(g["n_cloud"])
+    seen = {"matches": [], "iters": None, "n_src": None}
+    real_ransac, real_icp_batch = t3d.ransac_loop, ops.icp_batch
+
+    def ransac_spy(*a, **kw):
+        H, m = real_ransac(*a, **kw)
+        seen["matches"].append(np.array(m, dtype=np.int64))
+        return H, m
+
+    def icp_spy(s, so, *a, **kw):
+        r = real_icp_batch(s, so, *a, **kw)
+        seen["iters"] = r["iters"].cpu().numpy()
+        seen["n_src"] = np.diff(so.cpu().numpy())
+        return r
+
+    t3d.ransac_loop, ops.icp_batch = ransac_spy, icp_spy
+    try:
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            hs = rec.register_consecutive_pairs(clouds, gray, depth, filter_pts_frac=0.1, partial_set_frac=0.7)
+        print("configs[0], 7 pairs: %.2f s" % (time.perf_counter() - t0))
+    finally:
+        t3d.ransac_loop, ops.icp_batch = real_ransac, real_icp_batch
+    assert _digest(np.random.get_state()[1]) == g["rng_end"][0], "global RNG not consumed as the reference consumes it"
+    assert len(hs) == 7
+    assert [len(m) for m in seen["matches"]] == list(g["n_inliers"])
+    assert [_digest(m) for m in seen["matches"]] == list(g["match_hash"]), "RANSAC inlier lists differ from the reference's"
+    assert list(seen["n_src"]) == list(g["n_icp_src"])
+    assert list(seen["iters"]) == list(g["icp_iters"]), (seen["iters"], g["icp_iters"])
+    for k in range(7):
+        assert_transform_parity(hs[k], g["final_h"][k], O.scene_extent(clouds[k]), "sofa pair %d" % (k + 1))
+
+
+def test_kitchen_config1_both_pairs():
+    """BASELINE.json configs[1] IN FULL: the loop body of rigid3d_proc (reconstruct.py:260-283) on both pairs of
+    examples/kitchen_rgbd through the drop-ins q8.mathching_skimage (K5) -> q9.ransac_loop (K4A) -> r3d.rigid_transform_3D
+    (K3), against the recorded run of the reference (tests/golden/make_golden_configs.py)."""
+    import contextlib
+    import io
+    import warnings
+    cv2 = pytest.importorskip("cv2")
+    from conftest import load_golden
+    q8 = sub("utils.homography_utils.q8")
+    q9 = sub("utils.homography_utils.q9")
+    r3d = sub("utils.r3d")
+    g = load_golden("kitchen_config1")
+    gray, depth = g["gray"], g["depth"]
+    sift = cv2.xfeatures2d.SIFT_create() if hasattr(cv2, "xfeatures2d") else cv2.SIFT_create()
+    kps, des = zip(*[sift.detectAndCompute(img, None) for img in gray])
+    assert [len(k) for k in kps] == list(g["n_kp"])
+    np_kps = [np.array([(k.pt[0], k.pt[1]) for k in kp], dtype=int) for kp in kps]
+    kps_3d = [[(p[0], p[1], depth[i][p[1], p[0]]) for p in np_kps[i]] for i in range(len(depth))]
+    np.random.seed(0)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        for i in range(1, len(gray)):
+            bf = q8.mathching_skimage(gray[i], kps[i], des[i], gray[i - 1], kps[i - 1], des[i - 1], False)
+            assert len(bf) == g["n_bf"][i - 1]
+            H, fm = q9.ransac_loop(gray[i], gray[i - 1], kps[i], kps[i - 1], bf)
+            assert len(fm) == g["n_inliers"][i - 1]
+            assert _digest(np.array(fm, dtype=np.int64)) == g["match_hash"][i - 1], "RANSAC inlier list differs"
+            m1 = [kps_3d[i][m[0]] for m in fm]
+            m2 = [kps_3d[i - 1][m[1]] for m in fm]
+            R, t = r3d.rigid_transform_3D(np.array(m1).T, np.array(m2).T)
+            np.testing.assert_allclose(R, g["transforms"][i - 1][:3, :3], rtol=0, atol=1e-10)
+            np.testing.assert_allclose(t[:, 0], g["transforms"][i - 1][:3, 3], rtol=0, atol=1e-8)
+    assert _digest(np.random.get_state()[1]) == g["rng_end"][0]

@@ -196,3 +196,34 @@ def test_device_hypotheses_match_the_reference_estimators(kind):
     # device-resident sweep: counts of the device hypotheses = oracle counts of the same matrices
     counts = ops.ransac3d_score(Td, Pd, Qd).cpu().numpy()
     assert np.array_equal(counts[ok], O.score_hypotheses_3d(Th[ok], P, Q))
+
+
+def test_k4b_against_the_reference_golden():
+    """The pin of K4B (BASELINE.json configs[4] at 1/10 size, tests/golden/make_golden_k4b.py): 2 000 rigid and 2 000 affine
+    hypotheses x 5 000 correspondences.  Hypotheses, residuals and the < 10 threshold were computed by the reference's OWN
+    rigid_transform_3D / homo_rigid_transform_3d / get_transformed_points; the scoring kernel must return the same inlier
+    counts for the reference's hypotheses, and the hypothesis kernels (K6) the same matrices from the same samples."""
+    import torch
+    from conftest import load_golden
+    ops = sub("ops")
+    g = load_golden("k4b")
+    P, Q = g["P"].astype(np.float64), g["Q"]
+    Pd = ops.pack_xyzw(torch.from_numpy(P).cuda())
+    Qd = ops.pack_xyzw(torch.from_numpy(Q).cuda())
+    star = ops.ransac3d_score(torch.from_numpy(g["T_star"][None].copy()).cuda(), Pd, Qd).cpu().numpy()
+    assert int(star[0]) == int(g["count_star"])
+    for kind, T, want, samples in (("rigid", g["T_rigid"], g["counts_rigid"], g["samples3"]),
+                                   ("affine", g["T_affine"], g["counts_affine"], g["samples4"])):
+        fin = np.isfinite(T).all(axis=(1, 2))
+        got = ops.ransac3d_score(torch.from_numpy(np.ascontiguousarray(T[fin])).cuda(), Pd, Qd).cpu().numpy()
+        assert np.array_equal(got, want[fin]), "%s: %d of %d inlier counts differ from the reference's" % (
+            kind, (got != want[fin]).sum(), fin.sum())
+        Td, status = ops.hypotheses_3d(Pd, Qd, torch.from_numpy(samples).cuda(), kind)
+        Th, ok = Td.cpu().numpy(), (status.cpu().numpy() == 0) & fin
+        assert ok.sum() > 1950
+        scale = np.maximum(np.abs(T[ok]).max(axis=(1, 2), keepdims=True), 1.0)
+        err = np.abs(Th[ok] - T[ok]) / scale
+        assert np.median(err) < 1e-10 and err.max() < 1e-5, (kind, np.median(err), err.max())
+        # device-generated hypotheses near T* find (almost) the same consensus set; the bulk scores 0-2 inliers either way
+        dev_counts = ops.ransac3d_score(Td, Pd, Qd).cpu().numpy()
+        assert (np.abs(dev_counts[ok] - want[ok]) <= np.maximum(2, want[ok] // 50)).all()

@@ -230,3 +230,83 @@ def test_kitchen_pair_reference_run():
     R, t = O.rigid_transform_3D(g["kps3d_1"][fm[:, 0]].T, g["kps3d_2"][fm[:, 1]].T)
     np.testing.assert_allclose(R, g["R"], rtol=0, atol=1e-12)
     np.testing.assert_allclose(t, g["t"], rtol=0, atol=1e-9)
+
+
+def _digest(a):
+    import hashlib
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], dtype=np.uint64)[0]
+
+
+def test_k4b_golden_pins_the_3d_hypothesis_scoring():
+    """BASELINE.json configs[4] at 1/10 size: tests/golden/make_golden_k4b.py ran the composition SURVEY.md section 8(c)
+    defines with the reference's own rigid_transform_3D / homo_rigid_transform_3d / get_transformed_points and the < 10
+    threshold of q9.py:122.  The oracle must give the same hypotheses and the same inlier counts."""
+    g = load_golden("k4b")
+    P, Q = g["P"].astype(np.float64), g["Q"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        Tr = O.rigid_hypotheses(P, Q, g["samples3"][:300])
+        Ta = O.affine_hypotheses(P, Q, g["samples4"][:300])
+    np.testing.assert_allclose(Tr, g["T_rigid"][:300], rtol=0, atol=1e-9)
+    ok = np.isfinite(g["T_affine"][:300]).all(axis=(1, 2))
+    scale = np.maximum(np.abs(g["T_affine"][:300][ok]).max(axis=(1, 2), keepdims=True), 1.0)
+    assert (np.abs(Ta[ok] - g["T_affine"][:300][ok]) / scale).max() < 1e-9
+    assert int(O.score_hypotheses_3d(g["T_star"][None], P, Q)[0]) == int(g["count_star"]) == 2940
+    for T, want in ((g["T_rigid"], g["counts_rigid"]), (g["T_affine"], g["counts_affine"])):
+        fin = np.isfinite(T).all(axis=(1, 2))
+        assert fin.sum() > 1990
+        assert np.array_equal(O.score_hypotheses_3d(T[fin], P, Q), want[fin])
+        assert want[fin].max() > 2000 and (want[fin] > 100).sum() >= 15
+
+
+def test_kitchen_config1_both_pairs():
+    """BASELINE.json configs[1] IN FULL (tests/golden/make_golden_configs.py): SIFT keypoints, the loop body of
+    rigid3d_proc (reconstruct.py:260-283) for both pairs of examples/kitchen_rgbd, one np.random.seed(0) before the loop."""
+    import warnings
+    cv2 = pytest.importorskip("cv2")
+    g = load_golden("kitchen_config1")
+    gray, depth = g["gray"], g["depth"]
+    sift = cv2.xfeatures2d.SIFT_create() if hasattr(cv2, "xfeatures2d") else cv2.SIFT_create()
+    kps, des = zip(*[sift.detectAndCompute(img, None) for img in gray])
+    assert [len(k) for k in kps] == list(g["n_kp"])
+    np_kps = [np.array([(k.pt[0], k.pt[1]) for k in kp], dtype=int) for kp in kps]            # reconstruct.py:31
+    kps_3d = [np.array([(p[0], p[1], depth[i][p[1], p[0]]) for p in np_kps[i]]) for i in range(len(depth))]   # :52-59
+    np.random.seed(0)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        for i in range(1, len(gray)):
+            bf = O.match_descriptors_skimage(des[i], des[i - 1], max_ratio=0.8, cross_check=True)
+            assert len(bf) == g["n_bf"][i - 1]
+            H, fm = O.ransac_loop(gray[i], gray[i - 1], kps[i], kps[i - 1], bf)
+            assert len(fm) == g["n_inliers"][i - 1] and _digest(np.array(fm, dtype=np.int64)) == g["match_hash"][i - 1]
+            R, t = O.rigid_transform_3D(kps_3d[i][fm[:, 0]].T, kps_3d[i - 1][fm[:, 1]].T)
+            np.testing.assert_allclose(R, g["transforms"][i - 1][:3, :3], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(t[:, 0], g["transforms"][i - 1][:3, 3], rtol=0, atol=1e-9)
+    assert _digest(np.random.get_state()[1]) == g["rng_end"][0]
+
+
+def test_sofa_config0_all_seven_pairs():
+    """BASELINE.json configs[0] IN FULL (tests/golden/make_golden_configs.py): the pair loop of trans3d_proc
+    (reconstruct.py:319-329) on the 8 frames of examples/sofa_rgbd, filter_pts_frac 0.1, partial_set_frac 0.7, the global RNG
+    flowing from pair to pair.  The oracle reproduces the global stage of all 7 pairs (inlier sets by hash, the RNG end
+    state) and -- to keep the CPU suite short -- the ICP stage of the two pairs the reference converged fastest on."""
+    import warnings
+    pytest.importorskip("cv2")
+    g = load_golden("sofa_config0")
+    gray, depth = g["gray"], g["depth"]
+    clouds = [O.depth_to_voxel_ld(d) for d in depth]
+    assert [len(c) for c in clouds] == list(g["n_cloud"])
+    icp_pairs = set(np.argsort(g["icp_iters"])[:2])
+    np.random.seed(0)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        for i in range(1, len(clouds)):
+            rec = {}
+            out = O.register_imgs(gray[i], gray[i - 1], depth[i], depth[i - 1], clouds[i], clouds[i - 1], filter_pts_frac=0.1,
+                                  partial_set_frac=0.7, run_icp=(i - 1) in icp_pairs, record=rec)
+            assert len(rec["matches"]) == g["n_inliers"][i - 1]
+            assert _digest(np.array(rec["matches"], dtype=np.int64)) == g["match_hash"][i - 1]
+            assert rec["n_icp_src"] == g["n_icp_src"][i - 1]
+            if (i - 1) in icp_pairs:
+                assert rec["icp_iters"] == g["icp_iters"][i - 1]
+                np.testing.assert_allclose(out, g["final_h"][i - 1], rtol=0, atol=1e-8)
+    assert _digest(np.random.get_state()[1]) == g["rng_end"][0]
