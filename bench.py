@@ -8,7 +8,11 @@ ICP, sharded over 1/2/4/8 GPUs).
 
 A "step" registers every pair of the rank's batch once: K1 back-projection of both frames, grid
 build, 30 ICP iterations (tolerance 0, partial_set_size 1.0), one all-gather of the 4x4s when N > 1.
-Weak scaling: every GPU holds `--pairs` (default 1024) pairs; `value` counts all ranks' pairs.
+Weak scaling: every GPU holds `--pairs` (default 1024) pairs; `value` counts all ranks' pairs.  The same
+line also carries `strong` (ONE 1024-pair batch split over the N ranks), `secondary` (the other
+configurations of BASELINE.json, measured in the same run) and `parity`: the first pairs of the batch are the
+NumPy-generated frames of SURVEY.md section 8(d), the CPU arm registers exactly those, and the two sets of
+transforms are compared with north_star's tolerances -- the program exits non-zero when they differ.
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -45,10 +49,32 @@ def parse_args():
     ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "16")))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "3")))
     ap.add_argument("--partial", type=float, default=1.0)
-    ap.add_argument("--cpu-sample-iters", type=int, default=16,
-                    help="ICP iterations per pair of the bounded CPU sample (~1.3 s per iteration per core)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-iters", type=int, default=None,
+                    help="ICP iterations per pair of the bounded CPU sample (~0.45 s per iteration per core); default: 16 for the "
+                         "cpu_baseline leg of the CUDA arm, all 30 for --impl reference (no extrapolation)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="also skips the parity gate (it needs the CPU transforms)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary configurations (partial 0.7, configs[3], configs[4], K1)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: --pairs is the GLOBAL batch, split over the ranks, and is what `value` reports")
     return ap.parse_args()
+
+
+def make_config(args, world):
+    """The `config` object of the JSON line -- the same for both arms (the reference arm registers a bounded sample of it)."""
+    strong = args.scaling == "strong"
+    per_gpu = args.pairs // world if strong else args.pairs
+    return {"workload": "synthetic 640x480 depth-pair batch: pinhole back-projection + %d-iteration ICP (tolerance 0, "
+                        "partial_set_size %.2f), BASELINE.json configs[2]" % (ICP_ITERS, args.partial),
+            "pairs_per_gpu": per_gpu, "global_pairs": per_gpu * world, "icp_iterations": ICP_ITERS,
+            "inputs": "SURVEY.md 8(d) surface model; pair p < host cores (max 64) of rank 0 = np.random.default_rng(1234 + p) "
+                      "(2dto3dreconstruction_b200/synth.py), the frames both arms register and the parity gate compares",
+            "pairs_per_chunk": args.pairs_per_chunk, "streams": args.streams,
+            "parallelism": "pairs sharded x%d, one all-gather of 4x4s" % world,
+            "l2": "inputs %.2f GB per step per GPU (> 126 MB L2); no flush needed" % (2 * per_gpu * H * W * 2 / 1e9)}
+
+
+def n_shared_pairs(limit):
+    return max(1, min(os.cpu_count() or 1, 64, limit))
 
 
 def peak_hbm():
@@ -60,33 +86,9 @@ def peak_hbm():
 
 
 def synth_batch_torch(n_pairs, seed, device):
-    """The SURVEY.md section 8d surface model, generated on the device (NumPy would need ~20 s for
-    1024 pairs): frame a = surface + N(0,2), 10% dropout; frame b = surface shifted by integer
-    (du,dv) in [-8,8]^2 and dz in [-20,20], fresh noise and dropout.  uint16 [n,480,640] x 2."""
-    import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(1234 + seed)
-    u = torch.arange(W, device=device, dtype=torch.float32)[None, None, :]
-    v = torch.arange(H, device=device, dtype=torch.float32)[None, :, None]
-    a = torch.empty((n_pairs, H, W), dtype=torch.uint16, device=device)
-    b = torch.empty((n_pairs, H, W), dtype=torch.uint16, device=device)
-    step = 64
-    for s in range(0, n_pairs, step):
-        e = min(n_pairs, s + step)
-        k = e - s
-        du = torch.randint(-8, 9, (k, 1, 1), generator=g, device=device).float()
-        dv = torch.randint(-8, 9, (k, 1, 1), generator=g, device=device).float()
-        dz = torch.randint(-20, 21, (k, 1, 1), generator=g, device=device).float()
-        fa = 2000.0 + 600.0 * torch.sin(u / 97.0) + 400.0 * torch.cos(v / 61.0) + torch.randn((k, H, W), generator=g, device=device) * 2.0
-        fb = (2000.0 + 600.0 * torch.sin((u + du) / 97.0) + 400.0 * torch.cos((v + dv) / 61.0) + dz
-              + torch.randn((k, H, W), generator=g, device=device) * 2.0)
-        fa = torch.round(fa)
-        fb = torch.round(fb)
-        fa[torch.rand((k, H, W), generator=g, device=device) < 0.10] = 0
-        fb[torch.rand((k, H, W), generator=g, device=device) < 0.10] = 0
-        a[s:e] = fa.to(torch.int32).to(torch.uint16)
-        b[s:e] = fb.to(torch.int32).to(torch.uint16)
-    return a, b
+    """The SURVEY.md section 8(d) surface model drawn on the device (2dto3dreconstruction_b200/synth.py)."""
+    import importlib
+    return importlib.import_module("2dto3dreconstruction_b200.synth").depth_batch_device(n_pairs, seed, device)
 
 
 class ClockSampler:
@@ -136,36 +138,51 @@ class ClockSampler:
         return out
 
 
+def transform_gap(T, T_ref, extent):
+    """north_star's two numbers: Frobenius norm of the rotation difference, translation difference / scene extent."""
+    import numpy as np
+    T, T_ref = np.asarray(T), np.asarray(T_ref)
+    return float(np.linalg.norm(T[:3, :3] - T_ref[:3, :3])), float(np.linalg.norm(T[:3, 3] - T_ref[:3, 3]) / extent)
+
+
 def run_reference(args):
     """The reference's own CPU path (oracle port: NumPy + scikit-learn KD-tree, as utils/icp.py
-    calls them) on all host cores, same metric and config.  Rank 0 only."""
+    calls them) on all host cores, same metric and config.  Rank 0 only.  A step registers one pair per core -- the
+    very frames the CUDA arm's parity gate compares -- for all 30 iterations (~15 s per step).  With `--cpu-sample-iters k`
+    a step runs k of the 30 iterations and `value` scales the per-pair time; one untimed full pass then validates the
+    scaling (`full_run`; measured 2026-10: scaled / full = 0.988)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import numpy as np
+    import importlib
     from oracle import cpu_bench
-    from oracle import ref_port as O
-    cores = os.cpu_count() or 1
-    n = min(cores, 64)
-    frames = [O.synth_depth_pair(k) for k in range(n)]
-    fa = np.stack([f[0] for f in frames])
-    fb = np.stack([f[1] for f in frames])
-    vals, corr = [], []
+    synth = importlib.import_module("2dto3dreconstruction_b200.synth")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = n_shared_pairs(args.pairs)
+    fa, fb = synth.depth_pairs(0, n)
+    full = None
+    if args.cpu_sample_iters != ICP_ITERS:
+        full = cpu_bench.time_pairs(fa, fb, sample_iters=ICP_ITERS, full_iters=ICP_ITERS, partial=args.partial, cores=n)
+    vals, corr, walls = [], [], []
     for s in range(args.warmup + args.steps):
         r = cpu_bench.time_pairs(fa, fb, sample_iters=args.cpu_sample_iters, full_iters=ICP_ITERS, partial=args.partial,
                                  cores=n)
         if s >= args.warmup:
             vals.append(r["pairs_per_s"])
             corr.append(r["corr_per_s"])
+            walls.append(r["wall_s"])
     v = sum(vals) / len(vals)
     line = {
         "impl": "reference", "metric": "icp_frame_pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * n / v, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(walls) / len(walls), "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "correspondences_per_sec": sum(corr) / len(corr),
-        "config": {"workload": "synthetic 640x480 depth pairs: pinhole back-projection + %d-iteration ICP (tolerance 0, "
-                               "partial_set_size %.2f)" % (ICP_ITERS, args.partial), "pairs_per_step": n,
-                   "icp_iterations": ICP_ITERS},
+        "config": make_config(args, world),
+        "ms_per_step_note": "measured wall time of one step = %d pairs x %d of %d iterations; `value` = pairs / (per-pair time scaled "
+                            "to %d iterations)" % (n, args.cpu_sample_iters, ICP_ITERS, ICP_ITERS),
+        "full_run": None if full is None else {
+            "what": "the same %d pairs registered once for all %d iterations (untimed by the step clock)" % (n, ICP_ITERS),
+            "pairs_per_s": full["pairs_per_s"], "wall_s": full["wall_s"], "scaled_over_full": v / full["pairs_per_s"]},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -176,8 +193,12 @@ def run_reference(args):
 def main():
     args = parse_args()
     if args.impl == "reference":
+        if args.cpu_sample_iters is None:
+            args.cpu_sample_iters = ICP_ITERS
         run_reference(args)
         return
+    if args.cpu_sample_iters is None:
+        args.cpu_sample_iters = 16
     if args.warmup < 3:
         args.warmup = 3
 
@@ -203,8 +224,18 @@ def main():
     C.require_device()
     L = C.lib()
 
-    P = args.pairs
+    synth = importlib.import_module("2dto3dreconstruction_b200.synth")
+    strong = args.scaling == "strong"
+    if strong and args.pairs % world:
+        raise SystemExit("--scaling strong needs --pairs divisible by the number of ranks")
+    P = args.pairs // world if strong else args.pairs
     depth_a, depth_b = synth_batch_torch(P, seed=rank, device=dev)
+    n_shared = n_shared_pairs(P) if rank == 0 else 0
+    if n_shared:
+        # the pairs both arms register (SURVEY.md 8(d) NumPy generator); the rest of the batch is drawn on the device
+        np_a, np_b = synth.depth_pairs(0, n_shared)
+        depth_a[:n_shared] = torch.from_numpy(np_a).to(dev)
+        depth_b[:n_shared] = torch.from_numpy(np_b).to(dev)
     torch.cuda.synchronize()
     kw = dict(max_iterations=ICP_ITERS, tolerance=0.0, partial_set_size=args.partial,
               pairs_per_chunk=args.pairs_per_chunk, n_streams=args.streams)
@@ -286,11 +317,33 @@ def main():
     e2e_wall_ms = (time.perf_counter() - t0) * 1000.0
     parity_dev_host = bool(np.array_equal(rh["T"], out["T"].cpu().numpy()))
 
+    # ---------------- strong scaling beside the weak line: ONE `--pairs` batch split over the ranks ----------------
+    strong_ms = None
+    if world > 1 and not strong and args.pairs % world == 0:
+        Ps = args.pairs // world
+        sa, sb = depth_a[:Ps], depth_b[:Ps]
+
+        def step_strong():
+            r = pipeline.register_depth_pairs(sa, sb, **kw)
+            r["T_all"] = pipeline.gather_transforms(r["T"], Ps * world)
+            return r
+
+        for _ in range(3):
+            step_strong()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            step_strong()
+        s1.record()
+        barrier()
+        strong_ms = s0.elapsed_time(s1)
+
     # max over ranks
     if world > 1:
-        tt = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+        tt = torch.tensor([ms_total, e2e_ms, strong_ms or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = float(tt[0]), float(tt[1])
+        ms_total, e2e_ms, strong_ms = float(tt[0]), float(tt[1]), (float(tt[2]) if strong_ms else None)
         cc = torch.tensor([corr_per_step, launches], dtype=torch.int64, device=dev)
         dist.all_reduce(cc, op=dist.ReduceOp.SUM)
         corr_total, launches_total = int(cc[0]), int(cc[1])
@@ -345,27 +398,50 @@ def main():
         except Exception:
             pass
 
-    cpu_baseline = None
+    cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:
         from oracle import cpu_bench
-        cores = os.cpu_count() or 1
-        n = min(cores, P, 64)
-        fa = depth_a[:n].cpu().numpy()
-        fb = depth_b[:n].cpu().numpy()
-        r = cpu_bench.time_pairs(fa, fb, sample_iters=args.cpu_sample_iters, full_iters=ICP_ITERS, partial=args.partial, cores=n)
+        n = n_shared
+        r = cpu_bench.time_pairs(np_a, np_b, sample_iters=args.cpu_sample_iters, full_iters=ICP_ITERS, partial=args.partial, cores=n)
         cpu_baseline = {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
                         "sample": r["sample"], "correspondences_per_sec": r["corr_per_s"], "wall_s": r["wall_s"]}
+        # parity gate: the CUDA path on the very frames the CPU arm just registered, stopped after the
+        # same number of iterations, against the CPU transforms; north_star: |dR|_F <= 1e-4, |dt| <= 1e-4 x scene extent
+        g = pipeline.register_depth_pairs(depth_a[:n], depth_b[:n], max_iterations=args.cpu_sample_iters, tolerance=0.0,
+                                          partial_set_size=args.partial, pairs_per_chunk=args.pairs_per_chunk, n_streams=1)
+        Tg, itg, ng = g["T"].cpu().numpy(), g["iters"].cpu().numpy(), g["n_src"].cpu().numpy()
+        gaps = [transform_gap(Tg[k], r["results"][k]["T"], r["results"][k]["extent"]) for k in range(n)]
+        parity = {"pairs": n, "iterations": args.cpu_sample_iters, "max_dR": max(x[0] for x in gaps),
+                  "max_dt_over_extent": max(x[1] for x in gaps), "tolerance": 1e-4,
+                  "iters_equal": bool(all(int(itg[k]) == int(r["results"][k]["iters"]) for k in range(n))),
+                  "cloud_sizes_equal": bool(all(int(ng[k]) == int(r["results"][k]["n_src"]) for k in range(n))),
+                  "against": "oracle port (NumPy + scikit-learn KD-tree) on the same frames, same iteration count"}
+        parity["ok"] = bool(parity["max_dR"] <= 1e-4 and parity["max_dt_over_extent"] <= 1e-4 and parity["iters_equal"]
+                            and parity["cloud_sizes_equal"] and parity_dev_host)
+
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        # the other configurations of BASELINE.json, same run, same process (tools/bench_kernels.py: CUDA events, median of 5)
+        del depth_a, depth_b, host_a, host_b
+        pipeline._ws_cache.clear()
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_kernels
+        k = bench_kernels.run(["k1", "icp", "k4b", "configs3"], icp_partials=(args.partial, 0.7) if args.partial != 0.7 else (0.7,))
+        secondary = {
+            "partial_set_size_0.7": k.get("K2K3_icp_30it_partial_0.7"),
+            "partial_set_size_%.1f_same_8_pairs" % args.partial: k.get("K2K3_icp_30it_partial_%.1f" % args.partial),
+            "configs[3]": k.get("configs3_single_pair_2M"),
+            "configs[4]": k.get("K4B_ransac3d_sweep"),
+            "K1_backproject": k.get("K1_backproject"),
+        }
 
     line = {
         "metric": "icp_frame_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "correspondences_per_sec": corr_total / (ms_per_step / 1000.0),
-        "config": {"workload": "synthetic 640x480 depth-pair batch: pinhole back-projection + %d-iteration ICP (tolerance 0, "
-                               "partial_set_size %.2f), BASELINE.json configs[2]" % (ICP_ITERS, args.partial),
-                   "pairs_per_gpu": P, "global_pairs": pairs_total, "icp_iterations": ICP_ITERS, "pairs_per_chunk": args.pairs_per_chunk,
-                   "streams": args.streams, "parallelism": "pairs sharded x%d, one all-gather of 4x4s" % world,
-                   "l2": "inputs %.2f GB per step per GPU (> 126 MB L2); no flush needed" % (2 * P * H * W * 2 / 1e9)},
+        "config": make_config(args, world),
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(2 * P * H * W * 2) * world,
                 "d2h_bytes_per_step": int(P * (128 + 4 + 8 + 4 + 4)) * world, "ms_per_step": e2e_ms / args.steps,
                 "wall_ms_per_step_rank0": e2e_wall_ms / args.steps,
@@ -375,10 +451,20 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "parity": parity,
+        "secondary": secondary,
     }
+    if strong_ms is not None:
+        line["strong"] = {"global_pairs": args.pairs, "pairs_per_gpu": args.pairs // world, "ms_per_step": strong_ms / args.steps,
+                          "value": args.pairs / (strong_ms / args.steps / 1000.0), "unit": "pairs/s",
+                          "note": "one %d-pair batch split over the %d ranks, device-resident, all-gather included, max over ranks" % (
+                              args.pairs, world)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        print("PARITY GATE FAILED: %r" % (parity,), file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -78,6 +78,40 @@ def test_full_density_pair(partial):
     np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=0, atol=1e-4 * O.scene_extent(B))
 
 
+@pytest.mark.parametrize("partial", [1.0, 0.7])
+def test_bench_configuration_full_30_iterations(partial):
+    """The bench's own configuration (BASELINE.json configs[2]): one full-density 640x480 pair of the SURVEY.md 8(d)
+    generator, ALL 30 iterations with tolerance 0 -- i.e. including iterations 13-30, where most queries skip their
+    search on the exact bound of DESIGN.md section 4 -- against the oracle with the reference's KD-tree, at partial_set_size
+    1.0 (the bench) and 0.7 (the reference pipeline's setting).  Then the correspondences of the LAST iteration against
+    float64 brute force on the cloud the 29 previous iterations produced."""
+    from parity import assert_nn_parity
+    icp = sub("utils.icp")
+    ops = sub("ops")
+    C = sub("_capi")
+    a, b = O.synth_depth_pair(1)
+    A, B = O.depth_to_voxel_ld(a), O.depth_to_voxel_ld(b)
+    T, dist, it = icp.icp(A, B, max_iterations=30, tolerance=0.0, partial_set_size=partial)
+    Tr, dr, itr = O.icp(A, B, max_iterations=30, tolerance=0.0, partial_set_size=partial)
+    assert it == itr == 31
+    dR, dt = assert_transform_parity(T, Tr, O.scene_extent(B), "30 iterations, partial %.1f" % partial)
+    print("partial %.1f: |dR| %.2e, |dt| %.2e (extent %.0f)" % (partial, dR, dt, O.scene_extent(B)))
+    assert dist.shape == dr.shape
+    np.testing.assert_allclose(np.sort(dist), np.sort(dr), rtol=0, atol=1e-4 * O.scene_extent(B))
+    # last iteration: indices and distances of all queries vs brute force
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    so, do = ops._offsets([len(A)]), ops._offsets([len(B)])
+    r = ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=30, tolerance=0.0, partial_set_size=partial, want_last=True)
+    T29, _, _ = icp.icp(A, B, max_iterations=29, tolerance=0.0, partial_set_size=partial)
+    moved = O.get_transformed_points(A, T29)
+    db, ib = O.nearest_neighbor_brute_c(moved, B)
+    n_ties = assert_nn_parity(moved, B, r["idx"].cpu().numpy(), r["dist"].cpu().numpy(), ib, db, "last iteration")
+    assert n_ties < 200
+    keep = r["keep"].cpu().numpy().astype(bool)
+    assert keep.sum() == int(len(A) * partial)
+
+
 def test_batch_matches_single_and_is_deterministic():
     ops = sub("ops")
     C = sub("_capi")

@@ -163,3 +163,16 @@ def test_sharded_icp_exchange_callback_gloo(tmp_path, world):
     mp.spawn(_exchange_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(os.path.join(str(tmp_path), "rank%d" % r)).read() == "ok"
+
+
+def test_bench_workload_generator_equals_the_oracle_generator():
+    """bench.py's inputs (2dto3dreconstruction_b200/synth.py) are the SURVEY.md 8(d) NumPy frames the oracle generates:
+    both arms of the benchmark, and its parity gate, register the same pairs."""
+    from oracle import ref_port as O
+    synth = sub("synth")
+    for k, (h, w) in [(0, (480, 640)), (7, (480, 640)), (3, (96, 128))]:
+        a, b = synth.depth_pair(k, h, w)
+        a2, b2 = O.synth_depth_pair(k, h=h, w=w)
+        assert a.dtype == np.uint16 and np.array_equal(a, a2) and np.array_equal(b, b2)
+    fa, fb = synth.depth_pairs(5, 2, 48, 64)
+    assert np.array_equal(fa[1], O.synth_depth_pair(6, h=48, w=64)[0])
