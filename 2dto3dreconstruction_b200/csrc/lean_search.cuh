@@ -67,9 +67,12 @@ constexpr unsigned FULL = 0xffffffffu;
 //   4 segment lookup rounds   5 segments looked up              6 non-empty segments
 //   7 skipped lanes whose seed was beaten by an evaluated point (a violated bound: must stay 0)
 //   8 single-query (far) searches  9 their block-list sweep steps  10 their 32-point scan steps  11 block-granular walks
-//   12 sum of task durations (clock64)  13 longest task (clock64)          (8..13: r3d_nn_stats_read_ext)
+//   12 sum of task durations (clock64)  13 longest task (clock64)          (8..31: r3d_nn_stats_read_ext)
+//   neighbourhood cache (icp.cu): 16 tasks answered from the cache  17 records attempted  18 records kept  19 tasks sent back to
+//   the full search by an ambiguous fp32 minimum  20 tasks with every lane skipping  21 tasks whose record no longer covered a
+//   lane  22 scan trips (sum over tasks of the per-word maxima)  23 records dropped for overflow
 #ifdef R3D_NN_STATS
-static __device__ unsigned long long g_nn_stats[16];     // this header is included by icp.cu only
+static __device__ unsigned long long g_nn_stats[32];     // this header is included by icp.cu only
 #define R3D_STAT_MAX(slot, n)                                                               \
     do {                                                                                    \
         const unsigned long long _v = (unsigned long long)(n);                              \
@@ -104,12 +107,30 @@ __device__ __forceinline__ void eval_staged(Best& other, int seed_pos, const dou
     }
 }
 
+constexpr int CC_CAP = 128;      // candidates of one neighbourhood record (= bits of a lane's mask)
+
+// Neighbourhood record of a search (the neighbourhood cache of icp.cu), one per warp in shared memory.  In: `cc` (shared
+// memory, 1 + CC_CAP float4 owned by the warp) and the origin.  Out, per lane: R (0 = the lane is not covered) and the
+// range [cb, ce) of survivors recorded by the round of the cell walk that finished the lane: every point of the cloud
+// within R of the lane's query is among cc[1 + cb .. 1 + ce).  (Two rounds may record the same point twice; a lane only
+// ever looks at the candidates of its own round.)
+struct __align__(16) RecShared {
+    double ox, oy, oz;
+    float4* cc;
+    float R[32];
+    int range[32];      // cb | ce << 16
+};
+
 struct WarpList {
     double2* sxy;      // [LEAN_LIST_CAP] (x, y)
     double2* szw;      // [LEAN_LIST_CAP] (z, tag)
     int n;             // warp-uniform
     int nrep, rep;     // small pairs: every query sits on nrep = 4 (or 2) lanes, replica rep = lane / (32 / nrep); else nrep = 1, rep = 0
     double lo[3], hi[3];      // filter box (world coordinates)
+    // neighbourhood record (icp.cu, "neighbourhood cache"): while rs != nullptr every survivor of the filter box is also
+    // written, in stream order, to rs->cc[1 + k] as fp32 coordinates relative to rs->o + its sorted position
+    RecShared* rs;            // nullptr = not recording (everything else about the record lives in shared memory: registers are scarce here)
+    int cc_n;                 // survivors seen so far (the record is void when it exceeds CC_CAP)
 #if R3D_LEAN_TMA
     const double2* stage;     // two staging buffers of 32 raw 32-byte records each, filled by cp.async.bulk
     uint32_t stage_addr;      // shared-window address of `stage`
@@ -117,6 +138,19 @@ struct WarpList {
     unsigned phase;           // bit b: parity the next wait on mbarrier b uses
 #endif
 };
+
+// One survivor per keeping lane into the record, compacted by the ballot (warp-uniform call).
+__device__ __forceinline__ void cc_record(WarpList& L, bool keep, unsigned bal, unsigned lt, const double2 xy, const double2 zw) {
+    if (keep) {
+        const int c = L.cc_n + __popc(bal & lt);
+        if (c < CC_CAP) {
+            const RecShared* rs = L.rs;
+            rs->cc[1 + c] = make_float4((float)(xy.x - rs->ox), (float)(xy.y - rs->oy), (float)(zw.x - rs->oz),
+                                        __int_as_float(__double2hiint(zw.y)));
+        }
+    }
+    L.cc_n += __popc(bal);
+}
 
 // Every lane scans the list, four entries at a time.  Slots past n hold points of earlier batches (or
 // the point the list was initialised with): real points of the same cloud, harmless to re-evaluate.
@@ -265,6 +299,7 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 L.sxy[slot] = xy;
                 L.szw[slot] = zw;
             }
+            if (L.rs != nullptr) cc_record(L, keep, bal, lt, xy, zw);
             L.n += __popc(bal);
             if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
         }
@@ -293,6 +328,7 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 L.sxy[slot] = xy;
                 L.szw[slot] = zw;
             }
+            if (L.rs != nullptr) cc_record(L, keep, bal, lt, xy, zw);
             L.n += __popc(bal);
             if (t0 + 32 < total) fetch(t0 + 32);          // next batch's loads fly while the list is scanned
             if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
@@ -418,7 +454,9 @@ __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2
 
 __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, const Best& seed, Best& other, const GridView& v,
                                             const GridParams& g, bool active, double qx, double qy, double qz, float slack,
-                                            float& cover, int qpt = 32) {
+                                            float& cover, int qpt = 32, RecShared* rs = nullptr, int* rec_n = nullptr) {
+    // rs != nullptr (and 32 queries per task): record the survivors (RecShared above); *rec_n = their number if every active
+    // lane ended up covered and they fit, else -1 (warp-uniform)
     // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
     // margin: 2e-3 cells absolute plus 2.4e-7 relative to the coordinate (one float ulp), on top of the
     // 1e-6 relative slack of the radius.
@@ -440,6 +478,13 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
     // they evaluate, and are merged after every walk
     L.nrep = 32 / qpt;
     L.rep = (int)(threadIdx.x & 31) / qpt;
+    L.rs = qpt == 32 ? rs : nullptr;
+    L.cc_n = 0;
+    if (L.rs != nullptr) {
+        L.rs->R[threadIdx.x & 31] = 0.0f;
+        *rec_n = -1;
+    }
+    bool rec_bad = false;      // warp-uniform: a round looked at the whole grid (its survivors are unfiltered)
 #if R3D_LEAN_TMA
     L.stage = list + 2 * LEAN_LIST_CAP;
     L.stage_addr = smem_u32(L.stage);
@@ -458,6 +503,10 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
 #if R3D_LEAN_TMA
             tma_phase = L.phase;
 #endif
+            if (L.rs != nullptr) {
+                const bool covered = __all_sync(FULL, !active || L.rs->R[threadIdx.x & 31] > 0.0f);
+                if (covered && !rec_bad && L.cc_n <= CC_CAP) *rec_n = L.cc_n;
+            }
             return;
         }
         R3D_STAT(1, 1);
@@ -498,12 +547,20 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
             L.lo[0] = whole ? -CUDART_INF : (double)l0; L.hi[0] = whole ? CUDART_INF : (double)h0;
             L.lo[1] = whole ? -CUDART_INF : (double)l1; L.hi[1] = whole ? CUDART_INF : (double)h1;
             L.lo[2] = whole ? -CUDART_INF : (double)l2; L.hi[2] = whole ? CUDART_INF : (double)h2;
+            const int c0 = L.cc_n;
             lean_scan_box(L, other, seed.pos, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
             if (part) {
                 const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                 fin = whole || (rn <= ruse) || !(ruse < 1e37f);
                 if (fin) cover = whole ? inf : ruse;
                 rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the union) must not set the next radius
+            }
+            if (L.rs != nullptr) {
+                rec_bad = rec_bad || whole;
+                if (part && fin && ruse < 1e37f) {
+                    L.rs->R[threadIdx.x & 31] = ruse;
+                    L.rs->range[threadIdx.x & 31] = min(c0, 0xffff) | (min(L.cc_n, 0xffff) << 16);
+                }
             }
         } else {
             // far outliers / queries far outside the cloud / badly misaligned pairs: the served lanes are searched one

@@ -212,15 +212,18 @@ def test_search_skipping_and_search_variants_do_not_change_results():
         Tb = base["T"].cpu().numpy()
         # no skipping; generous slack; large cap; the tile search instead of the warp-union walk.  Every variant
         # is an exact search feeding the same fixed-order sums, so every bit must agree.
-        for opt, val in ((4, 0.0), (4, 64.0), (5, 1.0), (3, 2.0)):
-            assert L.r3d_set_option(opt, val) == 0
+        # (option 7 = the neighbourhood cache: off, and on with records taken early / late / with a huge skin)
+        for settings in (((4, 0.0),), ((4, 64.0),), ((5, 1.0),), ((3, 2.0),), ((7, 0.0),), ((7, 0.0), (4, 0.0)),
+                         ((4, 3.0), (5, 1.0)), ((4, 2.0), (5, 4.0)), ((4, 16.0), (5, 2.0)), ((4, 1.0), (5, 0.1))):
+            for opt, val in settings:
+                assert L.r3d_set_option(opt, val) == 0
             r = run(25)
-            assert np.array_equal(r["T"].cpu().numpy(), Tb), (opt, val)
-            assert np.array_equal(r["idx"].cpu().numpy(), base["idx"].cpu().numpy()), (opt, val)
-            assert np.array_equal(r["dist"].cpu().numpy(), base["dist"].cpu().numpy()), (opt, val)
-            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0)
+            assert np.array_equal(r["T"].cpu().numpy(), Tb), settings          # (17 k points: the neighbourhood cache is for larger pairs)
+            assert np.array_equal(r["idx"].cpu().numpy(), base["idx"].cpu().numpy()), settings
+            assert np.array_equal(r["dist"].cpu().numpy(), base["dist"].cpu().numpy()), settings
+            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0), L.r3d_set_option(7, 1.0)
     finally:
-        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0)
+        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0), L.r3d_set_option(7, 1.0)
     # the last iteration's correspondences against brute force: src of iteration 25 = T_24 * A, which is the
     # pose after 24 iterations
     T24 = run(24)["T"][0].cpu().numpy()
@@ -234,6 +237,87 @@ def test_search_skipping_and_search_variants_do_not_change_results():
         d_mine = np.linalg.norm(src[diff] - B[idx[diff]], axis=1)
         assert np.all(np.abs(d_mine - db[diff]) <= 1e-9 * np.maximum(db[diff], 1.0)), "wrong neighbour after skipping"
     assert diff.size < 0.001 * len(A)
+
+
+def _cache_case(kind):
+    rng = np.random.default_rng(5)
+    if kind == "depth":
+        a, b = O.synth_depth_pair(6, h=200, w=280)
+        fa = np.zeros((480, 640), np.uint16)
+        fb = np.zeros((480, 640), np.uint16)
+        fa[140:340, 180:460] = a
+        fb[140:340, 180:460] = b
+        return O.depth_to_voxel_ld(fa).astype(np.float64), O.depth_to_voxel_ld(fb).astype(np.float64)
+    if kind == "lattice":
+        # exact ties and duplicates: a square lattice (every point stored twice), queries on its cell centres and edges
+        gx, gy = np.meshgrid(np.arange(150.0), np.arange(150.0))
+        B = np.column_stack((gx.ravel() * 4.0, gy.ravel() * 4.0, np.zeros(gx.size)))
+        B = np.concatenate((B, B[::3]))
+        sx, sy = np.meshgrid(np.arange(0.0, 149.0, 0.5), np.arange(0.0, 149.0, 0.5))
+        A = np.column_stack((sx.ravel() * 4.0 + 2.0, sy.ravel() * 4.0, np.full(sx.size, 0.25)))
+        return A[:45000], B
+    # a smooth surface with continuous coordinates far from the origin
+    xy = rng.uniform(-300, 300, size=(60000, 2))
+    B = np.column_stack((xy, 40 * np.sin(xy[:, 0] / 60) * np.cos(xy[:, 1] / 45))) + 2.0e4
+    ang = 0.01
+    R = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    A = (B[rng.permutation(60000)[:40000]] - 2.0e4) @ R.T + np.array([2.0, -1.5, 1.0]) + rng.normal(size=(40000, 3)) * 0.3 + 2.0e4
+    return A, B
+
+
+@pytest.mark.parametrize("kind,partial", [("depth", 1.0), ("depth", 0.7), ("lattice", 1.0), ("far", 1.0), ("far", 0.6)])
+def test_neighbourhood_cache_does_not_change_results(kind, partial):
+    """The neighbourhood cache (csrc/icp.cu; pairs of more than 32 k source points) answers a task from the candidates its
+    last full search recorded: fp32 filter, fp64 decision, full search whenever the fp32 order is not decisive.  Whatever
+    the rule that decides when records are taken, every bit of the result -- transform, last iteration's indices and
+    distances, kept set -- must equal the run with the cache switched off; and the last iteration's neighbours must be
+    brute force's."""
+    from parity import assert_nn_parity
+    ops = sub("ops")
+    C = sub("_capi")
+    L = C.lib()
+    A, B = _cache_case(kind)
+    assert len(A) > 32768
+    s = ops.pack_xyzw(C.to_device(A))
+    d = ops.pack_xyzw(C.to_device(B))
+    so, do = ops._offsets([len(A)]), ops._offsets([len(B)])
+    iters = 8 if kind == "lattice" else 30
+
+    def run(n=iters):
+        return ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=n, tolerance=0.0, partial_set_size=partial, want_last=True)
+
+    def reset():
+        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(7, 1.0)
+
+    try:
+        assert L.r3d_set_option(7, 0.0) == 0
+        off = run()
+        for settings in (((7, 1.0),), ((7, 1.0), (4, 4.0), (5, 0.5)), ((7, 1.0), (4, 3.0), (5, 2.0)), ((7, 1.0), (4, 1.0), (5, 8.0)),
+                         ((7, 1.0), (4, 20.0), (5, 1.0))):
+            for opt, val in settings:
+                assert L.r3d_set_option(opt, val) == 0
+            on = run()
+            # Every search is exact, so the correspondences of every iteration are the same; what may differ is the ORDER in
+            # which the moment sums are added up (tasks answered by the light pass are summed in their own rows), i.e. the
+            # last bits of the transforms -- and, on exact distance ties, which of two equally near points is reported
+            assert np.array_equal(on["iters"].cpu().numpy(), off["iters"].cpu().numpy()), settings
+            np.testing.assert_allclose(on["T"].cpu().numpy(), off["T"].cpu().numpy(), rtol=0, atol=1e-9 * max(1.0, float(np.abs(B).max())))
+            np.testing.assert_allclose(on["dist"].cpu().numpy(), off["dist"].cpu().numpy(), rtol=1e-9, atol=1e-9)
+            same = on["idx"].cpu().numpy() == off["idx"].cpu().numpy()
+            assert same.mean() > (0.5 if kind == "lattice" else 0.9999), (same.mean(), settings)
+            assert np.abs(on["keep"].cpu().numpy().astype(int) - off["keep"].cpu().numpy().astype(int)).sum() <= (0 if partial == 1.0 else 4)
+            # ... and against brute force on the cloud this run's own first iters - 1 iterations produced
+            if settings == ((7, 1.0),):
+                moved_on = O.get_transformed_points(A, run(iters - 1)["T"][0].cpu().numpy())
+                db_on, ib_on = O.nearest_neighbor_brute_c(moved_on, B)
+                assert_nn_parity(moved_on, B, on["idx"].cpu().numpy(), on["dist"].cpu().numpy(), ib_on, db_on, kind + " (cache on)")
+            reset()
+        prev = run(iters - 1)["T"][0].cpu().numpy()
+    finally:
+        reset()
+    moved = O.get_transformed_points(A, prev)
+    db, ib = O.nearest_neighbor_brute_c(moved, B)
+    assert_nn_parity(moved, B, off["idx"].cpu().numpy(), off["dist"].cpu().numpy(), ib, db, kind)
 
 
 def test_fuzz_against_the_oracle_icp():

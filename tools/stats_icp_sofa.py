@@ -35,7 +35,7 @@ L.r3d_nn_timing_enable(0)
 print("factor %.2f: icp %.2f ms for %d iterations; nn kernel %.2f ms over %d launches (%.1f us each); mean dist %.3f" % (
     factor, dt * 1e3, iters, ms.value, n.value, 1e3 * ms.value / max(n.value, 1), d.mean()))
 if has_stats:
-    st = (ctypes.c_uint64 * 16)()
+    st = (ctypes.c_uint64 * 32)()
     L.r3d_nn_stats_read_ext(st, 1)
     tasks = max(int(st[0]), 1)
     print("per task: rounds %.2f, candidates/lane %.1f, lanes skipped %.2f, lookup rounds %.2f, segments %.1f, non-empty %.1f" % (

@@ -45,6 +45,8 @@ for cfg in configs.split(","):
     parts = cfg.split(":")
     impl, group, factor = parts[:3]
     mult, maxfrac = (parts[3], parts[4]) if len(parts) >= 5 else ("8", "0.25")
+    cache = parts[5] if len(parts) >= 6 else "1"
+    assert L.r3d_set_option(7, float(cache)) == 0
     assert L.r3d_set_option(4, float(mult)) == 0
     assert L.r3d_set_option(5, float(maxfrac)) == 0
     assert L.r3d_set_option(3, float(impl)) == 0
@@ -65,12 +67,12 @@ for cfg in configs.split(","):
         ref = T
     dev = float((T - ref).abs().max())
     nq = int(out["n_src"].sum())
-    print("impl %s G %2s factor %s slack %sx<=%s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
+    print("impl %s G %2s factor %s slack %sx<=%s cache %s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
           "%.2f G corr/s in kernel | max|T - T0| %.2e err0 %.6f" % (
-              impl, group, factor, mult, maxfrac, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
+              impl, group, factor, mult, maxfrac, cache, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
               nq * n.value / max(ms.value, 1e-9) / 1e6, dev, float(out["mean_err"][0])), flush=True)
     if stats_on:
-        sx = (ctypes.c_uint64 * 16)()
+        sx = (ctypes.c_uint64 * 32)()
         L.r3d_nn_stats_read_ext(sx, 1)
         st = list(sx)[:8]
         tasks = max(int(st[0]), 1)
