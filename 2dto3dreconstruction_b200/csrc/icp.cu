@@ -16,7 +16,6 @@
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
 #include "tile_search.cuh"
-#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -68,13 +67,7 @@ struct PairState {
     int done;
     int n_src;
     int cutoff;
-    int use_light;       // the next nn launch is preceded by nn_light_kernel for this pair (set by solve_kernel)
-};
-
-struct __align__(16) CacheHead {      // one task's neighbourhood record
-    double ox, oy, oz;     // origin of the fp32 coordinates
-    int n;                 // candidates recorded; -1 = no record
-    float spent;           // how far the task's queries have moved since the record was taken (upper bound)
+    int pad;
 };
 
 struct SelState {          // radix-select progress of one pair
@@ -97,7 +90,6 @@ struct IcpWorkspace {
     int src_rtiles;
     Point4* src_sorted;    // [pair][max_src]  source cloud in cell-key order, idx = original index
     int* vw_counter;       // [pair] next virtual warp of the running nn launch (reset by its consumer)
-    int* vw_counter2;      // [pair] the same for nn_light_kernel
     int32_t* nn_pos;       // [pair][max_src]  sorted position of the current neighbour
     float* budget;         // [pair][max_src]  lower bound of the distance from the query to every point but its neighbour
     double* d2;            // [pair][max_src]
@@ -105,13 +97,6 @@ struct IcpWorkspace {
     double* amom;          // [pair][16]  moments of A
     SelState* sel;         // [pair]
     uint32_t* sel_hist;    // [pair][SEL_PASSES][SEL_BINS]  zero between selections
-    // neighbourhood cache (see nn_query_kernel): per task of 32 queries the survivors of its last full search
-    int cc_tasks;          // tasks per pair = ceil(max_src / 32)
-    CacheHead* cc_head;    // [pair][cc_tasks]
-    float4* cc_pts;        // [pair][cc_tasks][CC_CAP]
-    float* cc_R;           // [pair][max_src]  radius around the query's position at record time that the record covers
-    uint4* cc_mask;        // [pair][max_src]  which of the task's candidates lie within that radius
-    uint8_t* task_todo;    // [pair][cc_tasks]  written by nn_light_kernel: 1 = the task still needs the full search
 };
 
 static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int max_src, int max_dst) {
@@ -123,7 +108,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
     w.src_rows = w.src_tiles * (NN_THREADS / 32);
-    if (w.src_rows < 2 * vwarps_for(max_src)) w.src_rows = 2 * vwarps_for(max_src);      // fused mode: rows [0, nvw) of the search kernel + [nvw, 2 nvw) of the light kernel
+    if (w.src_rows < vwarps_for(max_src)) w.src_rows = vwarps_for(max_src);
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
     w.src_desc = a.take<SortDesc>(P);
@@ -135,7 +120,6 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.shist = a.take<uint32_t>(P * 256 * w.src_rtiles);
     w.src_sorted = a.take<Point4>(P * max_src);
     w.vw_counter = a.take<int>(P);
-    w.vw_counter2 = a.take<int>(P);
     w.nn_pos = a.take<int32_t>(P * max_src);
     w.budget = a.take<float>(P * max_src);
     w.d2 = a.take<double>(P * max_src);
@@ -143,12 +127,6 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.amom = a.take<double>(P * 16);
     w.sel = a.take<SelState>(P);
     w.sel_hist = a.take<uint32_t>(P * SEL_PASSES * SEL_BINS);
-    w.cc_tasks = (max_src + 31) / 32;
-    w.cc_head = a.take<CacheHead>(P * w.cc_tasks);
-    w.cc_pts = a.take<float4>(P * w.cc_tasks * CC_CAP);
-    w.cc_R = a.take<float>(P * max_src);
-    w.cc_mask = a.take<uint4>(P * max_src);
-    w.task_todo = a.take<uint8_t>(P * w.cc_tasks);
     return a.used;
 }
 
@@ -168,7 +146,7 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     s.done = 0;
     s.n_src = src_off[pair + 1] - src_off[pair];
     s.cutoff = (int)((double)s.n_src * partial_set_size);   // int(N * p), utils/icp.py:109
-    s.use_light = 0;
+    s.pad = 0;
     if (s.n_src <= 0 || w.grid.params[pair].n_pts <= 0) s.done = 1;
     // int(N * p) == 0: the reference fits a transform to ZERO correspondences (means of empty arrays, SVD of NaN ->
     // LinAlgError).  Here such a pair does nothing and reports iters = 0, a value the loop cannot produce otherwise;
@@ -176,7 +154,6 @@ __global__ void state_init_kernel(IcpWorkspace w, const int32_t* __restrict__ sr
     if (s.cutoff <= 0 && !s.done) { s.done = 1; s.iters = 0; }
     w.state[pair] = s;
     w.vw_counter[pair] = 0;
-    w.vw_counter2[pair] = 0;
     w.src_desc[pair].n = s.n_src > 0 ? s.n_src : 0;
     w.src_desc[pair].n_passes = w.grid.params[pair].n_passes;
 }
@@ -320,173 +297,8 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
 struct LeanTuning {
     float slack_mult;        // slack = slack_mult * (movement of the query in this iteration) ...
     float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother)
-    int cache;               // neighbourhood cache on (seeded launches of the warp-union walk, 32 queries per task)
+    int group_max;           // tasks with at most this many searching lanes go through group_search (0 = never)
 };
-
-// ---- neighbourhood cache ------------------------------------------------------------------------------------
-// A full search of a task (32 consecutive queries) walks ~70 row segments of the grid to assemble the ~80-130 points
-// that lie in the union of its lanes' balls, and ICP then asks the same question again with every query moved by a
-// fraction of a point spacing.  So the search RECORDS what it assembled: the survivors of the filter box, as fp32
-// coordinates relative to a per-task origin + sorted position (CacheHead + cc_pts, one contiguous 1-2 KB range per
-// task), the radius R_i of the ball each lane asked for (cc_R) and, per lane, the bit mask of the candidates within
-// R_i of its query (cc_mask).  Every point of the cloud within R_i of the query's position at record time is in the
-// lane's mask.  Later iterations add up how far the task's queries have moved since (CacheHead::spent, the maximum over
-// the lanes, rounded up): a point within C_i = R_i - spent of the query's CURRENT position is still in the mask, so as
-// long as every searching lane's bound (the exact distance to its previous neighbour) is at most C_i the task is
-// answered from the record -- one bulk copy (TMA, cp.async.bulk + mbarrier) of the candidates into shared memory and a
-// per-lane walk over the set bits of its mask: ~10 candidates per lane instead of the union's ~80, no grid lookups.
-//   The walk is an fp32 FILTER: key = (bits of the fp32 squared distance, low 7 bits replaced by the candidate's
-// number), smallest and second smallest key per lane.  The fp32 distance is off by at most cc_err() (coordinates are
-// task-relative, a few tens of units) and the truncation by 2^-16 relative; when the runner-up's lower bound exceeds the
-// winner's upper bound the winner is THE nearest neighbour, strictly, and only it is evaluated in fp64 from its
-// original record (if it is the seed, nothing is: the seed's exact distance is already known).  Otherwise (exact ties,
-// duplicates, lattices) the task goes through the full fp64 search.  Results are therefore bit-identical to the search
-// without the cache, which tests/test_gpu_icp.py checks by switching it off (R3D_OPT_NN_CACHE).
-//   A record is taken when a task has to search anyway and its queries move slowly enough for the record to last
-// (the `slack` rule: R_i = bound + slack_mult x movement); all active lanes then search, so every lane is covered.
-__device__ __forceinline__ float cc_err(float M, float f) {
-    // |fp32 squared distance - exact| for operands rounded to fp32 from coordinates of magnitude <= M (relative to the
-    // record's origin): 2 sqrt(3) d (4 u M) + 5 u d^2 + 12 u^2 M^2 with u = 2^-24, every constant rounded up ~3x
-    return fmaf(1.2e-6f * M, sqrtf(f), fmaf(1.0e-6f, f, 1.0e-12f * M * M)) + 1e-30f;
-}
-constexpr float CC_TRUNC = 1.00002f;      // a key's distance bits are truncated by < 2^-16 relative
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Answer a task from its record (warp-wide call; see "neighbourhood cache" above).  `need`: the lane searches; its mask is at
-// mask_ptr, Rl its recorded radius.  Returns status 1 = answered -- then, for a lane that searched, (d2, idx, pos) is its new
-// neighbour evaluated in fp64 if that is not its seed (d2 = +inf if the seed stays), and lb_other a lower bound of the
-// distance to every candidate but the winner -- or status 0: some lane's fp32 order was not decisive, nothing is claimed.
-struct CcAnswer {
-    double d2;
-    int idx, pos;
-    float lb_other;
-    int status;
-};
-
-__device__ __forceinline__ CcAnswer cc_answer(const CacheHead* head, int hn, int oz_lo, int oz_hi, const float4* __restrict__ cc_task,
-                                           float4* cand, uint32_t bar, uint32_t parity, bool need, const uint4* __restrict__ mask_ptr,
-                                           float Rl, float spent, double qx, double qy, double qz, int seed_pos,
-                                           const Point4* __restrict__ pts) {
-    const int lane = threadIdx.x & 31;
-    const float inf = __int_as_float(0x7f800000);
-    __syncwarp();
-    if (lane == 0) {
-        cand[0] = make_float4(3.0e19f, 3.0e19f, 3.0e19f, __int_as_float(-1));      // squared distance = +inf
-        fence_proxy_async_smem();      // the buffer's last generic-proxy accesses come first
-        mbar_arrive_expect_tx(bar, (uint32_t)hn * 16u);
-        bulk_copy_g2s(smem_u32(cand + 1), cc_task, (uint32_t)hn * 16u, bar);
-    }
-    __syncwarp();
-    // while the copy flies: the origin, the query relative to it, the lane's mask
-    const double2 o01 = __ldg(reinterpret_cast<const double2*>(head));
-    const double o2 = __hiloint2double(oz_hi, oz_lo);
-    const float rx = (float)(qx - o01.x), ry = (float)(qy - o01.y), rz = (float)(qz - o2);
-    uint4 mk = make_uint4(0u, 0u, 0u, 0u);
-    if (need) mk = __ldg(mask_ptr);
-    const float M = 1.01f * (fabsf(rx) + fabsf(ry) + fabsf(rz) + spent + Rl);
-    int key1 = 0x7fffffff, key2 = 0x7fffffff;
-    mbar_wait(bar, parity);
-#ifdef R3D_NN_STATS
-    int trips = 0;
-#endif
-#pragma unroll
-    for (int wd = 0; wd < 4; wd++) {
-        unsigned m = wd == 0 ? mk.x : wd == 1 ? mk.y : wd == 2 ? mk.z : mk.w;
-        const int cnt = __reduce_max_sync(0xffffffffu, __popc(m));
-#ifdef R3D_NN_STATS
-        trips += cnt;
-#endif
-#pragma unroll 2
-        for (int t = 0; t < cnt; t++) {
-            const int c = m ? wd * 32 + __ffs(m) : 0;      // slot of the lane's next candidate; 0 = the point at infinity
-            m &= m - 1u;
-            const float4 pc = cand[c];
-            const float dx = rx - pc.x, dy = ry - pc.y, dz = rz - pc.z;
-            const float f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const int key = (__float_as_int(f) & ~127) | ((c - 1) & 127);
-            const int hi = max(key1, key);
-            key1 = min(key1, key);
-            key2 = min(key2, hi);
-        }
-    }
-    R3D_STAT(22, trips);
-    // winner / runner-up: is the fp32 order decisive?
-    const int c1 = key1 & 127;
-    const float f1 = __int_as_float(key1 & ~127), f2 = key2 == 0x7fffffff ? inf : __int_as_float(key2 & ~127);
-    const float up1 = fmaf(f1, CC_TRUNC, cc_err(M, f1 * CC_TRUNC));           // exact d2 of the winner <= up1
-    const float lo2 = f2 < inf ? f2 - cc_err(M, f2 * CC_TRUNC) : inf;          // exact d2 of everything else >= lo2
-    const bool ambiguous = need && !(lo2 > up1);
-    CcAnswer r;
-    r.d2 = CUDART_INF; r.idx = 0x7fffffff; r.pos = -1; r.lb_other = 0.0f; r.status = 0;
-    if (__any_sync(0xffffffffu, ambiguous)) {
-        R3D_STAT(19, 1);
-    } else {
-        R3D_STAT(16, 1);
-        r.status = 1;
-        if (need) {
-            const int pos1 = __float_as_int(cand[1 + c1].w);
-            if (pos1 == seed_pos) {
-                r.lb_other = sqrtf(fmaxf(lo2, 0.0f)) * 0.999999f;      // (inf stays inf)
-            } else {
-                Best o;
-                o.d2 = CUDART_INF; o.idx = 0x7fffffff; o.pos = -1;
-                consider(o, pts, pos1, qx, qy, qz);                   // the one fp64 evaluation
-                r.d2 = o.d2; r.idx = o.idx; r.pos = o.pos;
-                r.lb_other = sqrtf(__double2float_rd(o.d2));
-            }
-        }
-    }
-    __syncwarp();      // every lane is done with the buffer
-    return r;
-}
-
-// After a recorded full search (warp-wide call): per-lane masks of the candidates within the lane's radius, then masks, radii,
-// candidates and the head go to the pair's cache arrays.  n = survivors recorded (1 .. CC_CAP), all in rs->cc[1 .. n].
-__device__ __noinline__ void cc_store_record(CacheHead* head, float4* __restrict__ cc_task, const RecShared* rs, int n, bool active,
-                                             float* __restrict__ R_ptr, uint4* __restrict__ mask_ptr, double qx, double qy, double qz) {
-    const int lane = threadIdx.x & 31;
-    float4* cand = rs->cc;
-    const int n32 = (n + 31) & ~31;
-    for (int k = n + lane; k < n32; k += 32) cand[1 + k] = cand[0];      // pad the last mask word with points at infinity
-    __syncwarp();
-    // masks: candidates within R of the lane's query (fp32, conservative: an exact distance <= R passes)
-    const float R = rs->R[lane];
-    const int cb = rs->range[lane] & 0xffff, ce = rs->range[lane] >> 16;
-    const float rx = (float)(qx - rs->ox), ry = (float)(qy - rs->oy), rz = (float)(qz - rs->oz);
-    const float M = 1.01f * (fabsf(rx) + fabsf(ry) + fabsf(rz) + R);
-    const float R2 = R * R * 1.000002f;
-    const float thr = (active && R > 0.0f) ? R2 + cc_err(M, R2) : -1.0f;
-    unsigned mw[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int wd = 0; wd < 4; wd++) {
-        if (wd * 32 < n) {
-            unsigned m = 0u;
-#pragma unroll 8
-            for (int j = 0; j < 32; j++) {
-                const float4 pc = cand[1 + wd * 32 + j];
-                const float dx = rx - pc.x, dy = ry - pc.y, dz = rz - pc.z;
-                const float f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                m |= (f <= thr ? 1u : 0u) << j;
-            }
-            // only the candidates of the round that served this lane
-            const int lo = min(max(cb - wd * 32, 0), 32), hi = min(max(ce - wd * 32, 0), 32);
-            const unsigned below_hi = hi >= 32 ? 0xffffffffu : (1u << hi) - 1u;
-            const unsigned below_lo = lo >= 32 ? 0xffffffffu : (1u << lo) - 1u;
-            mw[wd] = m & below_hi & ~below_lo;
-        }
-    }
-    if (active) {
-        *R_ptr = R;
-        *mask_ptr = make_uint4(mw[0], mw[1], mw[2], mw[3]);
-    }
-    for (int k = lane; k < n; k += 32) cc_task[k] = cand[1 + k];
-    if (lane == 0) {
-        CacheHead h;
-        h.ox = rs->ox; h.oy = rs->oy; h.oz = rs->oz; h.n = n; h.spent = 0.0f;
-        *head = h;
-    }
-    __syncwarp();
-}
 
 #ifndef R3D_NN_PREFETCH
 #define R3D_NN_PREFETCH 0
@@ -495,9 +307,6 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 template <int IMPL> struct SearchSmem;
 template <> struct SearchSmem<1> { double2 list[LEAN_WARP_SMEM]; };      // survivors list; never shared with the reduction: its stale slots must stay real points
-// The neighbourhood cache's candidate buffer -- [0] = a point at infinity, [1 + c] = candidate c of the task's record -- lives
-// in the warp's moment-reduction scratch: the two are never live at the same time (a large L1 matters more to the walk)
-static_assert((1 + CC_CAP) * sizeof(float4) <= 8 * 33 * sizeof(double), "the candidate buffer must fit the reduction scratch");
 template <> struct SearchSmem<2> { TileWarp tile; };
 
 template <int IMPL, bool SEEDED, bool FUSED>
@@ -506,18 +315,16 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
     __shared__ double T[12], D[12];
-    __shared__ int s_n, s_done, s_light;
+    __shared__ int s_n, s_done;
     // the grid's base pointers live in shared memory: the compiler would otherwise recompute these 64-bit
     // addresses inside every loop of the search
     __shared__ GridView s_view;
     __shared__ __align__(16) double scratch[NN_THREADS / 32][8 * 33];      // moment reduction scratch (two passes of 8)
     __shared__ __align__(16) SearchSmem<IMPL> ssm[NN_THREADS / 32];
-    __shared__ RecShared rec_sh[IMPL == 1 ? NN_THREADS / 32 : 1];
     if (threadIdx.x == 0) {
         g = w.grid.params[pair];
         s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
-        s_light = w.state[pair].use_light;
         s_view = grid_view(w.grid, pair);
     }
     if (threadIdx.x < 12) {
@@ -534,15 +341,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
     const int qpt = queries_per_task(s_n);
     const int n_tasks = (s_n + qpt - 1) / qpt;
-    // neighbourhood cache: seeded launches of the warp-union walk, 32 queries per task
-    const bool use_cache = IMPL == 1 && SEEDED && tune.cache != 0 && qpt == 32;
-    CacheHead* cc_head = w.cc_head + (size_t)pair * w.cc_tasks;
-    float4* cc_pts = w.cc_pts + (size_t)pair * w.cc_tasks * CC_CAP;
-    float* cc_R = w.cc_R + (size_t)pair * w.max_src;
-    uint4* cc_mask = w.cc_mask + (size_t)pair * w.max_src;
-    // tasks nn_light_kernel has already answered in this iteration are not looked at again
-    const bool light_ran = use_cache && s_light != 0;
-    const uint8_t* task_todo = w.task_todo + (size_t)pair * w.cc_tasks;
     const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
@@ -569,7 +367,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         if (vw >= nvw) break;
         double acc = 0.0;      // lanes 0..15: running sum of moment `lane` over this virtual warp's tasks
         for (int task = vw; task < n_tasks; task += nvw) {
-            if (light_ran && task_todo[task] == 0) continue;      // answered by nn_light_kernel
             const int i = task * qpt + (lane & (qpt - 1));      // qpt < 32: 32 / qpt lanes per query (replicas)
             const bool active = i < s_n;
             const bool primary = lane < qpt;                    // the replica that writes the results
@@ -595,7 +392,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
             double sbx = 0.0, sby = 0.0, sbz = 0.0;      // coordinates of the seed
             float left = 0.0f, slack = 0.0f;      // bound on the other points left after this iteration's movement
-            float moved = 0.0f;                   // how far this query moved in this iteration (rounded up)
             bool skip = false;
             if (active) {
                 const Point4 a = load_point(src + i);
@@ -611,8 +407,8 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
                     // rounded up; the last term covers the fp64 rounding of the two transformed positions themselves
                     // (a few ulps of the coordinates), which matters only when coordinates are ~1e9 times the distances
-                    moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
-                            __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
+                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
+                                        __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
                     left = __fsub_rd(budget[i], moved);
                     skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
                     const float want = moved * tune.slack_mult;
@@ -625,46 +421,17 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
 #endif
             float cover = 0.0f, lb_other = 0.0f;
             if constexpr (IMPL == 1) {
-                bool record = false;        // warp-uniform: the full search below records the neighbourhood
-                if (use_cache) {
-                    // record the search if some lane has to search and every active lane moves slowly enough for the record
-                    // to last; whatever this task's old record was, it ends here (nn_light_kernel could not use it)
-                    const bool need_any = __any_sync(0xffffffffu, active && !skip);
-                    record = need_any && __all_sync(0xffffffffu, !active || slack > 0.0f);
-                    if (!record && lane == 0 && cc_head[task].n >= 0) cc_head[task].n = -1;
+                // tasks with few searching lanes: eight lanes per query on that query's own cells (group_search); everything
+                // else, and whatever the groups could not take, through the warp-union walk
+                unsigned walk_m = __ballot_sync(0xffffffffu, active && !skip);
+                if (SEEDED && qpt == 32 && walk_m != 0u && __popc(walk_m) <= tune.group_max)
+                    walk_m = group_search(walk_m, seed, other, v, g, qx, qy, qz, slack, cover);
+                if (walk_m != 0u) {
+                    float cover_w = 0.0f;
+                    lean_search(ssm[warp].list, phase, seed, other, v, g, active && !skip && ((walk_m >> lane) & 1u), qx, qy, qz, slack, cover_w, qpt);
+                    if ((walk_m >> lane) & 1u) cover = cover_w;
                 }
-                {
-                    RecShared* rs = nullptr;
-                    int rec_n = -1;
-                    if (record) {
-                        rs = &rec_sh[warp];
-                        // origin of the record: the first active lane's query, rounded to fp32 (any point near the task would do)
-                        const int lead = max(__ffs(__ballot_sync(0xffffffffu, active)) - 1, 0);
-                        const double ox = (double)(float)__shfl_sync(0xffffffffu, qx, lead);
-                        const double oy = (double)(float)__shfl_sync(0xffffffffu, qy, lead);
-                        const double oz = (double)(float)__shfl_sync(0xffffffffu, qz, lead);
-                        if (lane == 0) {
-                            rs->ox = ox; rs->oy = oy; rs->oz = oz;
-                            rs->cc = reinterpret_cast<float4*>(scratch[warp]);
-                            rs->cc[0] = make_float4(3.0e19f, 3.0e19f, 3.0e19f, __int_as_float(-1));
-                        }
-                        __syncwarp();
-                        // (when the search is recorded every active lane takes part, so that every lane is covered by the record)
-                        skip = false;
-                    }
-                    lean_search(ssm[warp].list, phase, seed, other, v, g, active && !skip, qx, qy, qz, slack, cover, qpt, rs, &rec_n);
-                    lb_other = sqrtf(__double2float_rd(other.d2));
-                    if (record) {
-                        R3D_STAT(17, 1);
-                        CacheHead* head = cc_head + task;
-                        if (rec_n > 0) {
-                            R3D_STAT(18, 1);
-                            cc_store_record(head, cc_pts + (size_t)task * CC_CAP, rs, rec_n, active, cc_R + i, cc_mask + i, qx, qy, qz);
-                        } else {
-                            if (lane == 0) head->n = -1;
-                        }
-                    }
-                }
+                lb_other = sqrtf(__double2float_rd(other.d2));
             } else {
                 // (the range queue shares the warp's reduction scratch: the two are never live at the same time)
                 static_assert(sizeof(scratch[0]) >= TILE_QUEUE_WORDS * sizeof(uint32_t), "the range queue lives in the reduction scratch");
@@ -713,157 +480,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             }
         }
         if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
-    }
-}
-
-// ---- the light pass of a seeded iteration -------------------------------------------------------------------
-// Before the search kernel, for pairs whose queries have slowed down (PairState::use_light, decided by solve_kernel):
-// the same tasks and virtual warps, but only the work that needs no grid walk -- the query's new position, the exact
-// distance to its previous neighbour, the skip test, and for tasks with a valid neighbourhood record the answer from the
-// record (cc_answer).  A task it can answer gets its results and moment sums here (rows [nvw, 2 nvw) of `partial`) and
-// task_todo = 0; every other task is left untouched with task_todo = 1 for nn_query_kernel.  Small and register-light
-// (no search code), so it runs at a higher occupancy than the search kernel: what it does is a chain of dependent loads.
-constexpr int LIGHT_THREADS = 128;
-#ifndef R3D_LIGHT_MIN_CTAS
-#define R3D_LIGHT_MIN_CTAS 10
-#endif
-
-template <bool FUSED>
-__global__ void __launch_bounds__(LIGHT_THREADS, R3D_LIGHT_MIN_CTAS)
-nn_light_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
-    const int pair = blockIdx.y;
-    __shared__ double T[12], D[12], shift[3];
-    __shared__ int s_n, s_run;
-    __shared__ __align__(16) double scratch[LIGHT_THREADS / 32][8 * 33];      // candidate buffer, then moment reduction scratch
-    __shared__ unsigned long long cc_bar[LIGHT_THREADS / 32];                 // completion of a record's bulk copy, one mbarrier per warp
-    if (threadIdx.x == 0) {
-        const PairState& st = w.state[pair];
-        s_n = st.n_src;
-        s_run = !st.done && st.use_light && queries_per_task(st.n_src) == 32;
-    }
-    if (threadIdx.x < 12) {
-        T[threadIdx.x] = w.state[pair].T[threadIdx.x];
-        D[threadIdx.x] = w.state[pair].T[threadIdx.x] - w.state[pair].Tp[threadIdx.x];
-    }
-    if (threadIdx.x < 3) shift[threadIdx.x] = w.grid.params[pair].shift[threadIdx.x];
-    __syncthreads();
-    if (!s_run) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Point4* pts = w.grid.sorted + (size_t)pair * w.grid.max_dst;
-    const Point4* src = w.src_sorted + (size_t)pair * w.max_src;
-    int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
-    float* budget = w.budget + (size_t)pair * w.max_src;
-    double* d2_out = w.d2 + (size_t)pair * w.max_src;
-    CacheHead* cc_head = w.cc_head + (size_t)pair * w.cc_tasks;
-    const float4* cc_pts = w.cc_pts + (size_t)pair * w.cc_tasks * CC_CAP;
-    const float* cc_R = w.cc_R + (size_t)pair * w.max_src;
-    const uint4* cc_mask = w.cc_mask + (size_t)pair * w.max_src;
-    uint8_t* task_todo = w.task_todo + (size_t)pair * w.cc_tasks;
-    const int n_tasks = (s_n + 31) / 32;
-    const int nvw = vwarps_for(s_n);
-    int* vw_counter = w.vw_counter2 + pair;
-    unsigned cc_phase = 0;
-    if (lane == 0) mbar_init(smem_u32(&cc_bar[warp]), 1);
-    mbar_init_fence();
-    __syncwarp();
-    const float inf = __int_as_float(0x7f800000);
-    while (true) {
-        int vw = 0;
-        if (lane == 0) vw = atomicAdd(vw_counter, 1);
-        vw = __shfl_sync(0xffffffffu, vw, 0) * w.shard_world + w.shard_rank;
-        if (vw >= nvw) break;
-        double acc = 0.0;
-        for (int task = vw; task < n_tasks; task += nvw) {
-            const int i = task * 32 + lane;
-            const bool active = i < s_n;
-            CacheHead* head = cc_head + task;
-            const int4 hw = __ldg(reinterpret_cast<const int4*>(head) + 1);      // {oz lo, oz hi, n, spent}
-            double qx = 0.0, qy = 0.0, qz = 0.0, sx = 0.0, sy = 0.0, sz = 0.0;
-            Best seed;
-            seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
-            float left = 0.0f, moved = 0.0f;
-            bool skip = false;
-            if (active) {
-                const int pos = nn_pos[i];
-                const float bud = budget[i];
-                const Point4 a = load_point(src + i);
-                qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
-                qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
-                qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-                consider_xyz(seed, sx, sy, sz, pts, pos, qx, qy, qz);
-                const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
-                const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
-                const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
-                // (the same expressions as nn_query_kernel: both must take the same skip decision)
-                moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
-                        __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
-                left = __fsub_rd(bud, moved);
-                skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
-            }
-            const bool need = active && !skip;
-            const unsigned need_m = __ballot_sync(0xffffffffu, need);
-            const int hn = hw.z;
-            // the task's movement since its record was taken: maximum over the lanes (non-negative floats order as integers)
-            const float mv_max = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(active ? moved : 0.0f)));
-            const float spent = __fadd_ru(__int_as_float(hw.w), mv_max);
-            bool answered = false;
-            Best other;
-            other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
-            float lb_other = 0.0f, cover = 0.0f;
-            R3D_STAT(0, 1);
-            if (need_m == 0u) {
-                R3D_STAT(20, 1);
-                answered = true;      // every lane keeps its neighbour
-            } else if (hn >= 0) {
-                // every point within C of the query's current position is in the lane's mask
-                const float Rl = need ? cc_R[i] : 0.0f;
-                const float C = need ? __fsub_rd(Rl, spent) : inf;
-                const float rho = sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
-                if (__all_sync(0xffffffffu, !need || rho <= C)) {
-                    const CcAnswer ans = cc_answer(head, hn, hw.x, hw.y, cc_pts + (size_t)task * CC_CAP, reinterpret_cast<float4*>(scratch[warp]),
-                                                   smem_u32(&cc_bar[warp]), cc_phase, need, cc_mask + i, Rl, spent, qx, qy, qz, seed.pos, pts);
-                    cc_phase ^= 1u;
-                    if (ans.status) {
-                        answered = true;
-                        if (need) {
-                            other.d2 = ans.d2; other.idx = ans.idx; other.pos = ans.pos;
-                            lb_other = ans.lb_other;
-                            cover = C;
-                        }
-                    }
-                } else {
-                    R3D_STAT(21, 1);
-                }
-            }
-            if (lane == 0) {
-                task_todo[task] = answered ? 0 : 1;
-                if (answered && hn >= 0) head->spent = spent;      // the record ages by this iteration's movement
-            }
-            if (!answered) continue;
-            R3D_STAT(3, __popc(__ballot_sync(0xffffffffu, active && skip)));
-            const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
-            const Best best = seed_wins ? seed : other;
-            if (active) {
-                if (!seed_wins) nn_pos[i] = best.pos;
-                if (!FUSED || write_d2) d2_out[i] = best.d2;
-                budget[i] = skip ? left : (seed_wins ? fminf(lb_other, cover) * 0.999999f : 0.0f);
-            }
-            if (FUSED) {
-                double m[16];
-#pragma unroll
-                for (int k = 0; k < 16; k++) m[k] = 0.0;
-                if (active) {
-                    if (!seed_wins) {
-                        const Point4 b = load_point(pts + best.pos);
-                        sx = b.x; sy = b.y; sz = b.z;
-                    }
-                    accumulate_pair(m, qx - shift[0], qy - shift[1], qz - shift[2], sx - shift[0], sy - shift[1], sz - shift[2],
-                                    sqrt(best.d2));
-                }
-                acc += warp_reduce16_small(m, scratch[warp]);
-            }
-        }
-        if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)(nvw + vw)) * 16 + lane] = acc;
     }
 }
 
@@ -1131,17 +747,16 @@ __device__ __forceinline__ void sum_rows16(const double* __restrict__ rows, int 
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS)
-solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed, LeanTuning tune) {
+solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     const int pair = blockIdx.x;
     PairState* st = w.state + pair;
-    if (threadIdx.x == 0) { w.vw_counter[pair] = 0; w.vw_counter2[pair] = 0; }      // the nn launches of this iteration have finished
+    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
     if (st->done) return;
     __shared__ double sm[SOLVE_THREADS];
     __shared__ double m[16];
     const int n = st->n_src;
-    // fused mode: one row per virtual warp of the search kernel, and as many again when the light pass ran for this
-    // pair (rows [nvw, 2 nvw)); otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? vwarps_for(n) * (st->use_light ? 2 : 1) : (n + 31) / 32;
+    // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
+    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32;
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -1156,27 +771,6 @@ solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed, LeanTuning tune) 
                 Tn[r * 4 + c] = acc;
             }
         }
-        // Should the next iteration start with the light pass?  It pays once records are being taken and budgets exist,
-        // i.e. once the queries of the iteration that just ended moved slowly enough for the record rule of the search
-        // kernel: its movement T - Tp, bounded over the corners of the destination cloud's bounding box (a heuristic for
-        // speed only: either way every task is answered exactly).
-        int light = 0;
-        if (tune.cache && queries_per_task(n) == 32) {
-            double mv2 = 0.0;
-            for (int c = 0; c < 8; c++) {
-                const double px = g.ox + ((c & 1) ? g.nx * g.cell : 0.0), py = g.oy + ((c & 2) ? g.ny * g.cell : 0.0),
-                             pz = g.oz + ((c & 4) ? g.nz * g.cell : 0.0);
-                double d2 = 0.0;
-                for (int r = 0; r < 3; r++) {
-                    const double d = (st->T[r * 4 + 0] - st->Tp[r * 4 + 0]) * px + (st->T[r * 4 + 1] - st->Tp[r * 4 + 1]) * py +
-                                     (st->T[r * 4 + 2] - st->Tp[r * 4 + 2]) * pz + (st->T[r * 4 + 3] - st->Tp[r * 4 + 3]);
-                    d2 += d * d;
-                }
-                mv2 = fmax(mv2, d2);
-            }
-            light = sqrt(mv2) * (double)tune.slack_mult <= 1.5 * (double)tune.slack_max_frac * g.cell;
-        }
-        st->use_light = light;
         for (int k = 0; k < 12; k++) { st->Tp[k] = st->T[k]; st->T[k] = Tn[k]; }
         const double mean = m[15] / cnt;
         st->mean_err = mean;
@@ -1322,19 +916,14 @@ static std::atomic<int> g_nn_impl{1};      // 1 = warp-union walk (lean_search.c
 static std::atomic<int> g_force_unfused{0}; // test knob: run partial_set_size == 1 through the select + moments kernels
 
 static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f};
-static std::atomic<int> g_nn_cache{1};      // neighbourhood cache of the seeded warp-union walk (results do not depend on it)
-
-static LeanTuning current_tuning() {
-    LeanTuning tune;
-    tune.slack_mult = g_slack_mult.load();
-    tune.slack_max_frac = g_slack_max_frac.load();
-    tune.cache = g_nn_cache.load() && g_nn_impl.load() == 1;
-    return tune;
-}
+static std::atomic<int> g_group_max{12};      // group_search for tasks with at most this many searching lanes (results do not depend on it)
 
 template <int IMPL>
 static int launch_query(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int write_d2, cudaStream_t st) {
-    const LeanTuning tune = current_tuning();
+    LeanTuning tune;
+    tune.slack_mult = g_slack_mult.load();
+    tune.slack_max_frac = g_slack_max_frac.load();
+    tune.group_max = g_group_max.load();
     if (seeded) {
         if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
         else R3D_LAUNCH((nn_query_kernel<IMPL, true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
@@ -1359,16 +948,6 @@ static int query_ctas_per_pair(const IcpWorkspace& w, int impl) {
 
 static int launch_nn(IcpWorkspace& w, bool seeded, bool fused, int write_d2, cudaStream_t st) {
     const int impl = g_nn_impl.load();
-    const LeanTuning tune = current_tuning();
-    if (seeded && tune.cache && queries_per_task(w.max_src) == 32) {
-        // the light pass first (pairs that are not ready for it leave at once): as many CTAs as are resident together
-        int per_pair = (148 * R3D_LIGHT_MIN_CTAS) / w.n_pairs;
-        const int cap = std::min((w.max_src + 32 * (LIGHT_THREADS / 32) - 1) / (32 * (LIGHT_THREADS / 32)), vwarps_for(w.max_src) / (LIGHT_THREADS / 32));
-        per_pair = std::max(1, std::min(per_pair, cap));
-        const dim3 lgrid(per_pair, w.n_pairs);
-        if (fused) R3D_LAUNCH((nn_light_kernel<true>), lgrid, LIGHT_THREADS, 0, st, w, write_d2, tune);
-        else R3D_LAUNCH((nn_light_kernel<false>), lgrid, LIGHT_THREADS, 0, st, w, write_d2, tune);
-    }
     const dim3 grid(query_ctas_per_pair(w, impl), w.n_pairs);
     if (impl == 1) return launch_query<1>(w, grid, seeded, fused, write_d2, st);
     return launch_query<2>(w, grid, seeded, fused, write_d2, st);
@@ -1403,7 +982,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
         w.shard_rank = shard->rank;
         w.shard_world = shard->world;
     }
-    const size_t shard_doubles = (size_t)vwarps_for(w.max_src) * 2 * 16;      // one pair (checked by the caller): rows [0, 2 nvw) (search + light pass)
+    const size_t shard_doubles = (size_t)vwarps_for(w.max_src) * 16;      // one pair (checked by the caller): rows [0, nvw)
     int rc = grid_build(w.grid, dst, dst_off, prm.cell_size, st);
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(state_init_kernel, (P + 127) / 128, 128, 0, st, w, src_off, init_pose, prm.partial_set_size);
@@ -1412,8 +991,6 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
     if (rc != R3D_OK) return rc;
     R3D_LAUNCH(src_moments_kernel, qgrid, NN_THREADS, 0, st, w);
     R3D_LAUNCH(src_moments_reduce_kernel, P, SOLVE_THREADS, 0, st, w);
-    // no task has a neighbourhood record yet (CacheHead::n = -1)
-    R3D_CUDA(cudaMemsetAsync(w.cc_head, 0xff, (size_t)P * w.cc_tasks * sizeof(CacheHead), st));
     const bool fused = prm.partial_set_size >= 1.0 && !g_force_unfused.load();
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
     if (!fused) R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * SEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
@@ -1438,7 +1015,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
             }
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
         }
-        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0, current_tuning());
+        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
     }
     R3D_LAUNCH(final_kernel, (P + 63) / 64, 64, 0, st, w, T_out, iters_out, mean_err_out);
     if ((last_idx || last_dist || last_keep) && prm.max_iterations > 0) {
@@ -1589,8 +1166,9 @@ extern "C" int r3d_set_option(int option, double value) {
             g_nn_impl.store(impl);
             return R3D_OK;
         }
-        case R3D_OPT_NN_CACHE:
-            g_nn_cache.store(value != 0.0 ? 1 : 0);
+        case R3D_OPT_GROUP_SEARCH_MAX:
+            if (!(value >= 0.0 && value <= 32.0)) return R3D_ERR_INVALID;
+            g_group_max.store((int)value);
             return R3D_OK;
         case R3D_OPT_FORCE_UNFUSED:
             g_force_unfused.store(value != 0.0 ? 1 : 0);

@@ -68,9 +68,8 @@ constexpr unsigned FULL = 0xffffffffu;
 //   7 skipped lanes whose seed was beaten by an evaluated point (a violated bound: must stay 0)
 //   8 single-query (far) searches  9 their block-list sweep steps  10 their 32-point scan steps  11 block-granular walks
 //   12 sum of task durations (clock64)  13 longest task (clock64)          (8..31: r3d_nn_stats_read_ext)
-//   neighbourhood cache (icp.cu): 16 tasks answered from the cache  17 records attempted  18 records kept  19 tasks sent back to
-//   the full search by an ambiguous fp32 minimum  20 tasks with every lane skipping  21 tasks whose record no longer covered a
-//   lane  22 scan trips (sum over tasks of the per-word maxima)  23 records dropped for overflow
+//   group search: 16 tasks searched by groups  17 group passes (4 queries each)  18 queries sent on to the union walk
+//   19 candidate steps (8 points per group each)
 #ifdef R3D_NN_STATS
 static __device__ unsigned long long g_nn_stats[32];     // this header is included by icp.cu only
 #define R3D_STAT_MAX(slot, n)                                                               \
@@ -107,30 +106,12 @@ __device__ __forceinline__ void eval_staged(Best& other, int seed_pos, const dou
     }
 }
 
-constexpr int CC_CAP = 128;      // candidates of one neighbourhood record (= bits of a lane's mask)
-
-// Neighbourhood record of a search (the neighbourhood cache of icp.cu), one per warp in shared memory.  In: `cc` (shared
-// memory, 1 + CC_CAP float4 owned by the warp) and the origin.  Out, per lane: R (0 = the lane is not covered) and the
-// range [cb, ce) of survivors recorded by the round of the cell walk that finished the lane: every point of the cloud
-// within R of the lane's query is among cc[1 + cb .. 1 + ce).  (Two rounds may record the same point twice; a lane only
-// ever looks at the candidates of its own round.)
-struct __align__(16) RecShared {
-    double ox, oy, oz;
-    float4* cc;
-    float R[32];
-    int range[32];      // cb | ce << 16
-};
-
 struct WarpList {
     double2* sxy;      // [LEAN_LIST_CAP] (x, y)
     double2* szw;      // [LEAN_LIST_CAP] (z, tag)
     int n;             // warp-uniform
     int nrep, rep;     // small pairs: every query sits on nrep = 4 (or 2) lanes, replica rep = lane / (32 / nrep); else nrep = 1, rep = 0
     double lo[3], hi[3];      // filter box (world coordinates)
-    // neighbourhood record (icp.cu, "neighbourhood cache"): while rs != nullptr every survivor of the filter box is also
-    // written, in stream order, to rs->cc[1 + k] as fp32 coordinates relative to rs->o + its sorted position
-    RecShared* rs;            // nullptr = not recording (everything else about the record lives in shared memory: registers are scarce here)
-    int cc_n;                 // survivors seen so far (the record is void when it exceeds CC_CAP)
 #if R3D_LEAN_TMA
     const double2* stage;     // two staging buffers of 32 raw 32-byte records each, filled by cp.async.bulk
     uint32_t stage_addr;      // shared-window address of `stage`
@@ -138,19 +119,6 @@ struct WarpList {
     unsigned phase;           // bit b: parity the next wait on mbarrier b uses
 #endif
 };
-
-// One survivor per keeping lane into the record, compacted by the ballot (warp-uniform call).
-__device__ __forceinline__ void cc_record(WarpList& L, bool keep, unsigned bal, unsigned lt, const double2 xy, const double2 zw) {
-    if (keep) {
-        const int c = L.cc_n + __popc(bal & lt);
-        if (c < CC_CAP) {
-            const RecShared* rs = L.rs;
-            rs->cc[1 + c] = make_float4((float)(xy.x - rs->ox), (float)(xy.y - rs->oy), (float)(zw.x - rs->oz),
-                                        __int_as_float(__double2hiint(zw.y)));
-        }
-    }
-    L.cc_n += __popc(bal);
-}
 
 // Every lane scans the list, four entries at a time.  Slots past n hold points of earlier batches (or
 // the point the list was initialised with): real points of the same cloud, harmless to re-evaluate.
@@ -299,7 +267,6 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 L.sxy[slot] = xy;
                 L.szw[slot] = zw;
             }
-            if (L.rs != nullptr) cc_record(L, keep, bal, lt, xy, zw);
             L.n += __popc(bal);
             if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
         }
@@ -328,7 +295,6 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 L.sxy[slot] = xy;
                 L.szw[slot] = zw;
             }
-            if (L.rs != nullptr) cc_record(L, keep, bal, lt, xy, zw);
             L.n += __popc(bal);
             if (t0 + 32 < total) fetch(t0 + 32);          // next batch's loads fly while the list is scanned
             if (L.n >= LEAN_FLUSH) list_flush(L, best, seed_pos, qx, qy, qz);
@@ -454,9 +420,7 @@ __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2
 
 __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, const Best& seed, Best& other, const GridView& v,
                                             const GridParams& g, bool active, double qx, double qy, double qz, float slack,
-                                            float& cover, int qpt = 32, RecShared* rs = nullptr, int* rec_n = nullptr) {
-    // rs != nullptr (and 32 queries per task): record the survivors (RecShared above); *rec_n = their number if every active
-    // lane ended up covered and they fit, else -1 (warp-uniform)
+                                            float& cover, int qpt = 32) {
     // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
     // margin: 2e-3 cells absolute plus 2.4e-7 relative to the coordinate (one float ulp), on top of the
     // 1e-6 relative slack of the radius.
@@ -478,13 +442,6 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
     // they evaluate, and are merged after every walk
     L.nrep = 32 / qpt;
     L.rep = (int)(threadIdx.x & 31) / qpt;
-    L.rs = qpt == 32 ? rs : nullptr;
-    L.cc_n = 0;
-    if (L.rs != nullptr) {
-        L.rs->R[threadIdx.x & 31] = 0.0f;
-        *rec_n = -1;
-    }
-    bool rec_bad = false;      // warp-uniform: a round looked at the whole grid (its survivors are unfiltered)
 #if R3D_LEAN_TMA
     L.stage = list + 2 * LEAN_LIST_CAP;
     L.stage_addr = smem_u32(L.stage);
@@ -503,10 +460,6 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
 #if R3D_LEAN_TMA
             tma_phase = L.phase;
 #endif
-            if (L.rs != nullptr) {
-                const bool covered = __all_sync(FULL, !active || L.rs->R[threadIdx.x & 31] > 0.0f);
-                if (covered && !rec_bad && L.cc_n <= CC_CAP) *rec_n = L.cc_n;
-            }
             return;
         }
         R3D_STAT(1, 1);
@@ -547,20 +500,12 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
             L.lo[0] = whole ? -CUDART_INF : (double)l0; L.hi[0] = whole ? CUDART_INF : (double)h0;
             L.lo[1] = whole ? -CUDART_INF : (double)l1; L.hi[1] = whole ? CUDART_INF : (double)h1;
             L.lo[2] = whole ? -CUDART_INF : (double)l2; L.hi[2] = whole ? CUDART_INF : (double)h2;
-            const int c0 = L.cc_n;
             lean_scan_box(L, other, seed.pos, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
             if (part) {
                 const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                 fin = whole || (rn <= ruse) || !(ruse < 1e37f);
                 if (fin) cover = whole ? inf : ruse;
                 rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the union) must not set the next radius
-            }
-            if (L.rs != nullptr) {
-                rec_bad = rec_bad || whole;
-                if (part && fin && ruse < 1e37f) {
-                    L.rs->R[threadIdx.x & 31] = ruse;
-                    L.rs->range[threadIdx.x & 31] = min(c0, 0xffff) | (min(L.cc_n, 0xffff) << 16);
-                }
             }
         } else {
             // far outliers / queries far outside the cloud / badly misaligned pairs: the served lanes are searched one
@@ -581,6 +526,138 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
             }
         }
     }
+}
+
+
+// ---- group search ---------------------------------------------------------------------------------------------
+// The union walk above costs about the same whether 32 lanes of a task search or two: rounds, ~70 segment lookups and a
+// candidate stream for the union box come first.  Once ICP has nearly converged most lanes keep their neighbour without a
+// search (nn_query_kernel's skip test) and the tasks that are left have a handful of searching lanes each.  Those are served
+// here: the warp splits into four groups of eight lanes and every group works for ONE searching query at a time -- the
+// (y, z) rows of the cells under that query's own ball, cut at block borders, are looked up one per lane (at most two
+// rounds of eight), their points are loaded eight at a time, one per lane, evaluated in fp64 and reduced over the group.
+// Same contract as lean_search for the lanes it serves (bit `lane` of `todo`; every one of them seeded, i.e. with a finite
+// bound): `other` = lexicographic minimum of (squared distance, cloud index) over every point but the seed within the
+// ball of radius `cover` = bound + slack.  Returns the lanes it did NOT serve (their ball spans more than GRP_SEGS_MAX row
+// segments): the caller sends those through lean_search.
+constexpr int GRP_SEGS_MAX = 16;
+
+__device__ __forceinline__ unsigned group_search(unsigned todo, const Best& seed, Best& other, const GridView& v, const GridParams& g,
+                                                 double qx, double qy, double qz, float slack, float& cover) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane >> 3, t = lane & 7;
+    // the lane's own ball as a box of cells (the arithmetic and margins of lean_search)
+    const float tqx = (float)((qx - g.ox) * g.inv_cell), tqy = (float)((qy - g.oy) * g.inv_cell),
+                tqz = (float)((qz - g.oz) * g.inv_cell);
+    const float mgx = fmaf(fabsf(tqx), 2.4e-7f, 2e-3f), mgy = fmaf(fabsf(tqy), 2.4e-7f, 2e-3f),
+                mgz = fmaf(fabsf(tqz), 2.4e-7f, 2e-3f);
+    const float rl = sqrtf((float)seed.d2) * 1.000001f + 1e-30f;
+    const float ruse = rl + slack;
+    const float rc = ruse * ((float)g.inv_cell * 1.000001f);
+    const int mlox = cell_lo(tqx - rc - mgx, g.nx), mhix = cell_hi(tqx + rc + mgx, g.nx);
+    const int mloy = cell_lo(tqy - rc - mgy, g.ny), mhiy = cell_hi(tqy + rc + mgy, g.ny);
+    const int mloz = cell_lo(tqz - rc - mgz, g.nz), mhiz = cell_hi(tqz + rc + mgz, g.nz);
+    const int mseg = (mhiy - mloy + 1) * (mhiz - mloz + 1) * ((mhix >> 2) - (mlox >> 2) + 1);
+    const bool mine = ((todo >> lane) & 1u) != 0u;
+    unsigned rem = __ballot_sync(FULL, mine && ruse < 1e30f && mseg <= GRP_SEGS_MAX);
+    const unsigned unserved = todo & ~rem;
+    R3D_STAT(16, rem ? 1 : 0);
+    R3D_STAT(18, __popc(unserved));
+    while (rem) {
+        R3D_STAT(17, 1);
+        // the next four searching lanes, one per group
+        const int o0 = __ffs(rem) - 1;
+        rem &= rem - 1u;
+        const int o1 = __ffs(rem) - 1;      // (-1 once rem is exhausted: rem & (rem - 1) stays 0)
+        rem &= rem - 1u;
+        const int o2 = __ffs(rem) - 1;
+        rem &= rem - 1u;
+        const int o3 = __ffs(rem) - 1;
+        rem &= rem - 1u;
+        const int owner = grp == 0 ? o0 : grp == 1 ? o1 : grp == 2 ? o2 : o3;
+        const int src = max(owner, 0);
+        const double ax = __shfl_sync(FULL, qx, src), ay = __shfl_sync(FULL, qy, src), az = __shfl_sync(FULL, qz, src);
+        const int lox = __shfl_sync(FULL, mlox, src), hix = __shfl_sync(FULL, mhix, src);
+        const int loy = __shfl_sync(FULL, mloy, src), hiy = __shfl_sync(FULL, mhiy, src);
+        const int loz = __shfl_sync(FULL, mloz, src), hiz = __shfl_sync(FULL, mhiz, src);
+        const int spos = __shfl_sync(FULL, seed.pos, src);
+        const int ny = hiy - loy + 1, bx0 = lox >> 2, nxb = (hix >> 2) - bx0 + 1;
+        const int nseg = owner >= 0 ? ny * (hiz - loz + 1) * nxb : 0;
+        const float inv_nxb = 1.0f / (float)nxb, inv_ny = 1.0f / (float)ny;
+        Best loc;
+        loc.d2 = CUDART_INF; loc.idx = 0x7fffffff; loc.pos = -1;
+#pragma unroll 1
+        for (int base_seg = 0; __any_sync(FULL, base_seg < nseg); base_seg += 8) {
+            const int sidx = base_seg + t;
+            uint32_t s = 0, cnt = 0;
+            if (sidx < nseg) {
+                // sidx = (k2 * ny + k1) * nxb + k0; quotients of small integers by reciprocal, then fixed up
+                int row = (int)((float)sidx * inv_nxb);
+                row += (sidx - row * nxb >= nxb) - (sidx - row * nxb < 0);
+                const int k0 = sidx - row * nxb;
+                int k2 = (int)((float)row * inv_ny);
+                k2 += (row - k2 * ny >= ny) - (row - k2 * ny < 0);
+                const int k1 = row - k2 * ny;
+                const int cbx = bx0 + k0, iy = loy + k1, iz = loz + k2;
+                const int cby = iy >> 2, cbz = iz >> 2;
+                const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
+                const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
+                if (b >= 0) {
+                    const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
+                    const uint32_t* cs = v.cell_start + (size_t)b * 64 + (((iz & 3) << 4) | ((iy & 3) << 2));
+                    s = __ldg(cs + x0);
+                    cnt = __ldg(cs + x1 + 1) - s;
+                }
+            }
+            // the group's candidate stream = concatenation of its eight segments
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, incl, o, 8);
+                if (t >= o) incl += y;
+            }
+            const uint32_t excl = incl - cnt;
+            const uint32_t total = __shfl_sync(FULL, incl, 7, 8);
+#pragma unroll 1
+            for (uint32_t base = 0; __any_sync(FULL, base < total); base += 8) {
+                R3D_STAT(19, 1);
+                const uint32_t tc = base + (uint32_t)t;
+                const bool have = tc < total;
+                const uint32_t tcc = min(tc, total - 1u);      // (total = 0: have is false and the position is not used)
+                int seg = 0;
+#pragma unroll
+                for (int step = 4; step >= 1; step >>= 1) {
+                    const uint32_t ex = __shfl_sync(FULL, excl, seg + step, 8);
+                    if (ex <= tcc) seg += step;
+                }
+                const uint32_t pos = __shfl_sync(FULL, s, seg, 8) + (tcc - __shfl_sync(FULL, excl, seg, 8));
+                if (have) {
+                    double2 xy, zw;
+                    load_record(v.pts + pos, xy, zw);
+                    const double dx = ax - xy.x, dy = ay - xy.y, dz = az - zw.x;
+                    const double d2 = dx * dx + dy * dy + dz * dz;
+                    const int idx = __double2loint(zw.y);
+                    if ((int)pos != spos && (d2 < loc.d2 || (d2 == loc.d2 && idx < loc.idx))) { loc.d2 = d2; loc.idx = idx; loc.pos = (int)pos; }
+                }
+            }
+        }
+        // lexicographic minimum over the group, then to the owner
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double od2 = __shfl_xor_sync(FULL, loc.d2, o);
+            const int oidx = __shfl_xor_sync(FULL, loc.idx, o), opos = __shfl_xor_sync(FULL, loc.pos, o);
+            if (od2 < loc.d2 || (od2 == loc.d2 && oidx < loc.idx)) { loc.d2 = od2; loc.idx = oidx; loc.pos = opos; }
+        }
+        const int gi = lane == o0 ? 0 : lane == o1 ? 1 : lane == o2 ? 2 : lane == o3 ? 3 : -1;
+        const int from = gi >= 0 ? gi * 8 : lane;
+        const double rd2 = __shfl_sync(FULL, loc.d2, from);
+        const int ridx = __shfl_sync(FULL, loc.idx, from), rpos = __shfl_sync(FULL, loc.pos, from);
+        if (gi >= 0) {
+            if (rd2 < other.d2 || (rd2 == other.d2 && ridx < other.idx)) { other.d2 = rd2; other.idx = ridx; other.pos = rpos; }
+            cover = ruse;
+        }
+    }
+    return unserved;
 }
 
 }  // namespace r3d

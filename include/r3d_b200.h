@@ -274,12 +274,12 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
  *                          how much larger than its bound a seeded search ball is made: a multiple of the query's movement in
  *                          this iteration (default 8), used while that is at most a fraction of the cell edge (default 0.25);
  *                          a multiple of 0 disables the skipping of searches that cannot change the neighbour
- *   R3D_OPT_NN_CACHE       1 (default) / 0: the neighbourhood cache of the ICP loop's search (csrc/icp.cu): a task of 32 queries
- *                          records the candidates its full search assembled and later iterations answer from that record (one
- *                          TMA bulk copy + a per-lane fp32 filter with an fp64 decision) while the queries have not left it */
+ *   R3D_OPT_GROUP_SEARCH_MAX  0..32 (default 12): seeded tasks of the ICP loop in which at most this many of the 32 lanes still
+ *                          search are served by csrc/lean_search.cuh group_search (eight lanes per query, only that query's
+ *                          own cells) instead of the warp-union walk; 0 = always the union walk */
 typedef enum {
     R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5, R3D_OPT_FORCE_UNFUSED = 6,
-    R3D_OPT_NN_CACHE = 7
+    R3D_OPT_GROUP_SEARCH_MAX = 7
 } r3d_option;
 int r3d_set_option(int option, double value);
 
@@ -298,7 +298,7 @@ int r3d_nn_timing_read(double* total_ms, int64_t* launches, int64_t* queries, in
  * evaluations per lane, searches skipped (lanes), segment lookup rounds, segments looked up, non-empty
  * segments, skipped lanes whose seed was beaten by an evaluated point (must be 0).  Synchronous. */
 int r3d_nn_stats_read(uint64_t* out8_host, int reset);
-int r3d_nn_stats_read_ext(uint64_t* out32_host, int reset);   /* 32 counters: + far-path / task-duration / neighbourhood-cache counters (csrc/lean_search.cuh) */
+int r3d_nn_stats_read_ext(uint64_t* out32_host, int reset);   /* 32 counters: + far-path / task-duration / group-search counters (csrc/lean_search.cuh) */
 
 #ifdef __cplusplus
 }

@@ -212,18 +212,18 @@ def test_search_skipping_and_search_variants_do_not_change_results():
         Tb = base["T"].cpu().numpy()
         # no skipping; generous slack; large cap; the tile search instead of the warp-union walk.  Every variant
         # is an exact search feeding the same fixed-order sums, so every bit must agree.
-        # (option 7 = the neighbourhood cache: off, and on with records taken early / late / with a huge skin)
-        for settings in (((4, 0.0),), ((4, 64.0),), ((5, 1.0),), ((3, 2.0),), ((7, 0.0),), ((7, 0.0), (4, 0.0)),
-                         ((4, 3.0), (5, 1.0)), ((4, 2.0), (5, 4.0)), ((4, 16.0), (5, 2.0)), ((4, 1.0), (5, 0.1))):
+        # (option 7 = group search for tasks with at most that many searching lanes: never / always)
+        for settings in (((4, 0.0),), ((4, 64.0),), ((5, 1.0),), ((3, 2.0),), ((7, 0.0),), ((7, 32.0),), ((7, 32.0), (4, 0.0)),
+                         ((4, 3.0), (5, 1.0)), ((4, 16.0), (5, 2.0), (7, 4.0))):
             for opt, val in settings:
                 assert L.r3d_set_option(opt, val) == 0
             r = run(25)
-            assert np.array_equal(r["T"].cpu().numpy(), Tb), settings          # (17 k points: the neighbourhood cache is for larger pairs)
+            assert np.array_equal(r["T"].cpu().numpy(), Tb), settings          # (17 k points: four queries per task, no group search)
             assert np.array_equal(r["idx"].cpu().numpy(), base["idx"].cpu().numpy()), settings
             assert np.array_equal(r["dist"].cpu().numpy(), base["dist"].cpu().numpy()), settings
-            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0), L.r3d_set_option(7, 1.0)
+            L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0), L.r3d_set_option(7, 12.0)
     finally:
-        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0), L.r3d_set_option(7, 1.0)
+        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(3, 1.0), L.r3d_set_option(7, 12.0)
     # the last iteration's correspondences against brute force: src of iteration 25 = T_24 * A, which is the
     # pose after 24 iterations
     T24 = run(24)["T"][0].cpu().numpy()
@@ -266,12 +266,12 @@ def _cache_case(kind):
 
 
 @pytest.mark.parametrize("kind,partial", [("depth", 1.0), ("depth", 0.7), ("lattice", 1.0), ("far", 1.0), ("far", 0.6)])
-def test_neighbourhood_cache_does_not_change_results(kind, partial):
-    """The neighbourhood cache (csrc/icp.cu; pairs of more than 32 k source points) answers a task from the candidates its
-    last full search recorded: fp32 filter, fp64 decision, full search whenever the fp32 order is not decisive.  Whatever
-    the rule that decides when records are taken, every bit of the result -- transform, last iteration's indices and
-    distances, kept set -- must equal the run with the cache switched off; and the last iteration's neighbours must be
-    brute force's."""
+def test_group_search_does_not_change_results(kind, partial):
+    """Tasks of a seeded iteration in which only a few lanes still search are served by group_search (csrc/lean_search.cuh:
+    eight lanes per query, only that query's own cells; pairs of more than 32 k source points) instead of the warp-union
+    walk.  Both are exact searches feeding the same fixed-order sums: whatever the threshold between them -- never, the
+    default, always -- every bit of the result (transform, last iteration's indices, distances and kept set) must be the
+    same, and the last iteration's neighbours must be brute force's."""
     from parity import assert_nn_parity
     ops = sub("ops")
     C = sub("_capi")
@@ -287,30 +287,17 @@ def test_neighbourhood_cache_does_not_change_results(kind, partial):
         return ops.icp_batch(s, so, d, do, 1, len(A), len(B), max_iterations=n, tolerance=0.0, partial_set_size=partial, want_last=True)
 
     def reset():
-        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(7, 1.0)
+        L.r3d_set_option(4, 8.0), L.r3d_set_option(5, 0.25), L.r3d_set_option(7, 12.0)
 
     try:
         assert L.r3d_set_option(7, 0.0) == 0
         off = run()
-        for settings in (((7, 1.0),), ((7, 1.0), (4, 4.0), (5, 0.5)), ((7, 1.0), (4, 3.0), (5, 2.0)), ((7, 1.0), (4, 1.0), (5, 8.0)),
-                         ((7, 1.0), (4, 20.0), (5, 1.0))):
+        for settings in (((7, 12.0),), ((7, 32.0),), ((7, 4.0), (4, 4.0), (5, 0.5)), ((7, 32.0), (4, 20.0), (5, 2.0)), ((7, 32.0), (4, 0.0))):
             for opt, val in settings:
                 assert L.r3d_set_option(opt, val) == 0
             on = run()
-            # Every search is exact, so the correspondences of every iteration are the same; what may differ is the ORDER in
-            # which the moment sums are added up (tasks answered by the light pass are summed in their own rows), i.e. the
-            # last bits of the transforms -- and, on exact distance ties, which of two equally near points is reported
-            assert np.array_equal(on["iters"].cpu().numpy(), off["iters"].cpu().numpy()), settings
-            np.testing.assert_allclose(on["T"].cpu().numpy(), off["T"].cpu().numpy(), rtol=0, atol=1e-9 * max(1.0, float(np.abs(B).max())))
-            np.testing.assert_allclose(on["dist"].cpu().numpy(), off["dist"].cpu().numpy(), rtol=1e-9, atol=1e-9)
-            same = on["idx"].cpu().numpy() == off["idx"].cpu().numpy()
-            assert same.mean() > (0.5 if kind == "lattice" else 0.9999), (same.mean(), settings)
-            assert np.abs(on["keep"].cpu().numpy().astype(int) - off["keep"].cpu().numpy().astype(int)).sum() <= (0 if partial == 1.0 else 4)
-            # ... and against brute force on the cloud this run's own first iters - 1 iterations produced
-            if settings == ((7, 1.0),):
-                moved_on = O.get_transformed_points(A, run(iters - 1)["T"][0].cpu().numpy())
-                db_on, ib_on = O.nearest_neighbor_brute_c(moved_on, B)
-                assert_nn_parity(moved_on, B, on["idx"].cpu().numpy(), on["dist"].cpu().numpy(), ib_on, db_on, kind + " (cache on)")
+            for key in ("T", "iters", "idx", "dist", "keep"):
+                assert np.array_equal(on[key].cpu().numpy(), off[key].cpu().numpy()), (key, settings)
             reset()
         prev = run(iters - 1)["T"][0].cpu().numpy()
     finally:

@@ -31,9 +31,9 @@ L.r3d_set_option(3, float(impl))
 if os.environ.get("SLACK"):      # "mult,maxfrac"
     mult, frac = (float(x) for x in os.environ["SLACK"].split(","))
     L.r3d_set_option(4, mult), L.r3d_set_option(5, frac)
-L.r3d_set_option(7, float(os.environ.get("CACHE", "1")))
+L.r3d_set_option(7, float(os.environ.get("GROUP", "12")))
 per_lane = 32.0 if impl == 2 else 1.0      # the tile search counts evaluations summed over the lanes
-print("iter  launch_us  rounds/task  searching lanes/task  candidates/lane  | per task: cached  all-skip  recorded(ok/tried)  uncovered  ambiguous  overflow  scan trips/cached task | mean_err")
+print("iter  launch_us  rounds/task  searching lanes/task  candidates/lane  | per task: group-searched  passes  steps  sent on to the walk (lanes) | mean_err")
 for k in range(1, iters + 1):
     kw = dict(max_iterations=k, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)
     best = None
@@ -53,8 +53,7 @@ for k in range(1, iters + 1):
     cur = [int(x) for x in st]
     d = [c - p for c, p in zip(cur, prev)]
     tasks = max(d[0], 1)
-    print("%4d  %9.1f  %11.2f  %20.2f  %15.1f  | %6.3f  %6.3f  %6.3f/%6.3f  %6.3f  %7.4f  %7.4f  %6.1f | %.6f" % (
-        k, 1e3 * (best - prev_ms), d[1] / tasks, 32 - d[3] / tasks, d[2] / tasks / per_lane, d[16] / tasks, d[20] / tasks,
-        d[18] / tasks, d[17] / tasks, d[21] / tasks, d[19] / tasks, d[23] / tasks, d[22] / max(d[16], 1),
-        float(out["mean_err"][0])), flush=True)
+    print("%4d  %9.1f  %11.2f  %20.2f  %15.1f  | %6.3f  %6.3f  %6.3f  %6.3f | %.6f" % (
+        k, 1e3 * (best - prev_ms), d[1] / tasks, 32 - d[3] / tasks, d[2] / tasks / per_lane, d[16] / tasks, d[17] / tasks,
+        d[19] / tasks, d[18] / tasks, float(out["mean_err"][0])), flush=True)
     prev_ms, prev = best, cur

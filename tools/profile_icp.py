@@ -28,7 +28,7 @@ C.lib().r3d_set_option(3, float(impl))
 if os.environ.get("SLACK"):      # "mult,maxfrac"
     mult, frac = (float(x) for x in os.environ["SLACK"].split(","))
     C.lib().r3d_set_option(4, mult), C.lib().r3d_set_option(5, frac)
-C.lib().r3d_set_option(7, float(os.environ.get("CACHE", "1")))
+C.lib().r3d_set_option(7, float(os.environ.get("GROUP", "12")))
 a, b = bench.synth_batch_torch(pairs, 0, torch.device("cuda", 0))
 kw = dict(max_iterations=iters, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)
 l0 = C.launch_count()
