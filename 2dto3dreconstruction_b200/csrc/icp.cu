@@ -34,6 +34,7 @@ constexpr int NN_THREADS = 128;
 constexpr int SEL_PASSES = 6;
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_TILE = 4096;      // keys per CTA of the histogram kernel
+constexpr int FSEL_PASSES = 2;      // histogram passes of the large-pair selection (11 bits of the fp32 key each)
 constexpr int NN_VWARPS = 2048;      // virtual warps per pair of the persistent nn kernel (see nn_kernel) ...
 constexpr int NN_VWARPS_BIG = 8192;  // ... and for a pair of more than NN_VWARPS_BIG_FROM source points: a single large pair must
 constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A function of the pair alone, so batching stays irrelevant.
@@ -78,6 +79,13 @@ struct SelState {          // radix-select progress of one pair
     int pad;
 };
 
+struct FSel {              // selection of a large pair: where the k-th smallest squared distance lies
+    uint32_t prefix;       // after pass p: the top 11 (p + 1) bits of its fp32 key
+    uint32_t k;            // its rank among the keys that share the prefix
+    uint32_t all;          // cutoff >= n: everything is kept
+    uint32_t pad;
+};
+
 struct IcpWorkspace {
     GridWorkspace grid;
     int shard_rank, shard_world;      // query sharding of r3d_icp_batch_sharded: this process runs virtual warps rank, rank + world, ...
@@ -96,7 +104,11 @@ struct IcpWorkspace {
     double* partial;       // [pair][src_rows][16]  one row of moment sums per query warp
     double* amom;          // [pair][16]  moments of A
     SelState* sel;         // [pair]
-    uint32_t* sel_hist;    // [pair][SEL_PASSES][SEL_BINS]  zero between selections
+    uint32_t* sel_hist;    // [pair][FSEL_PASSES][SEL_BINS]  zero between selections
+    FSel* fsel;            // [pair]  selection state of the large pairs
+    uint32_t* fsel_done;   // [pair][FSEL_PASSES]  histogram CTAs that have finished (the last one picks); zero between selections
+    uint32_t* cand_n;      // [pair]  correspondences inside the bracket of the k-th smallest distance ...
+    int32_t* cand_idx;     // [pair][max_src]  ... and their (sorted) source positions, in arrival order
 };
 
 static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int max_src, int max_dst) {
@@ -107,7 +119,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.shard_world = 1;
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
-    w.src_rows = w.src_tiles * (NN_THREADS / 32);
+    w.src_rows = w.src_tiles * (NN_THREADS / 32) + 1;      // (+ 1: the bracket row of fsel_resolve_kernel)
     if (w.src_rows < vwarps_for(max_src)) w.src_rows = vwarps_for(max_src);
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
@@ -126,7 +138,11 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.partial = a.take<double>(P * w.src_rows * 16);
     w.amom = a.take<double>(P * 16);
     w.sel = a.take<SelState>(P);
-    w.sel_hist = a.take<uint32_t>(P * SEL_PASSES * SEL_BINS);
+    w.sel_hist = a.take<uint32_t>(P * FSEL_PASSES * SEL_BINS);
+    w.fsel = a.take<FSel>(P);
+    w.fsel_done = a.take<uint32_t>(P * FSEL_PASSES);
+    w.cand_n = a.take<uint32_t>(P);
+    w.cand_idx = a.take<int32_t>(P * max_src);
     return a.used;
 }
 
@@ -492,47 +508,106 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
 __host__ __device__ __forceinline__ int sel_shift(int pass) { return pass == 0 ? 55 : 55 - 11 * pass; }
 __host__ __device__ __forceinline__ int sel_bits(int pass) { return pass == 0 ? 9 : 11; }
 
+// ---- selection of a large pair: two histogram passes on an fp32 key, a bracket, an exact finish ------------------
+// The k-th smallest of n squared distances (n up to millions) used to take six histogram + six pick launches on the 64-bit
+// keys.  Now: key32 = bits of the distance rounded TOWARDS ZERO to fp32 -- a monotone map, so the k-th smallest double has the
+// k-th smallest key32 -- and two histogram passes (11 bits each; the last CTA of a pass to finish scans the 2048 bins and
+// picks, no separate launch) leave a BRACKET: the distances whose key32 shares the 22 leading bits of the k-th one's, a
+// relative width of 2^-13, a few dozen of 276 k.  Everything below the bracket is kept for certain and its moments are summed
+// by fsel_moments_kernel in the same pass that lists the bracket's members; fsel_resolve_kernel then orders the members by
+// (distance, position) exactly, keeps the first k', publishes tau / idx_cut (kept() below) and adds their moments as one more
+// row.  Exact ties at the cutoff keep the lowest positions, as before; a bracket that holds many points (lattices: every
+// distance the same double) takes a slower, still exact route through fsel_resolve_kernel.
+__device__ __forceinline__ uint32_t key32(double d2) { return __float_as_uint(__double2float_rz(d2)); }
+
 __global__ void __launch_bounds__(256)
-sel_hist_kernel(IcpWorkspace w, int pass) {
+fsel_hist_kernel(IcpWorkspace w, int pass) {
     const int pair = blockIdx.y;
     const PairState* st = w.state + pair;
-    const SelState sel = w.sel[pair];
     const int n = st->n_src;
-    if (st->done || st->cutoff >= n || st->cutoff <= 0 || n <= NN_SMALL_PAIR) return;      // nothing to select (see sel_pick_step) / small pair
-    if (pass > 0 && sel.finished) return;
+    if (st->done || n <= NN_SMALL_PAIR) return;
     const int base = blockIdx.x * SEL_TILE;
     if (base >= n) return;
+    FSel* fs = w.fsel + pair;
+    const int cutoff = st->cutoff;
+    if (cutoff >= n) {      // nothing to select: everything is kept
+        if (blockIdx.x == 0 && threadIdx.x == 0) { fs->all = 1u; fs->prefix = 0u; fs->k = 0u; }
+        return;
+    }
     __shared__ uint32_t hist[SEL_BINS];
+    __shared__ uint32_t warp_tot[8];
+    __shared__ int s_last;
     for (int k = threadIdx.x; k < SEL_BINS; k += 256) hist[k] = 0;
     __syncthreads();
-    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(w.d2 + (size_t)pair * w.max_src);
-    const int shift = sel_shift(pass);
-    const uint32_t mask = (1u << sel_bits(pass)) - 1u;
-    const int lane = threadIdx.x & 31;
+    const double* d2 = w.d2 + (size_t)pair * w.max_src;
+    const uint32_t prefix = pass == 0 ? 0u : fs->prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 4
     for (int r = 0; r < SEL_TILE / 256; r++) {
         const int i = base + r * 256 + threadIdx.x;
         bool in = false;
         uint32_t d = 0;
         if (i < n) {
-            const unsigned long long key = keys[i];
-            in = (pass == 0) || ((key >> (shift + sel_bits(pass))) == sel.prefix);
-            d = (uint32_t)(key >> shift) & mask;
+            const uint32_t key = key32(d2[i]);
+            in = pass == 0 || (key >> 21) == prefix;
+            d = pass == 0 ? key >> 21 : (key >> 10) & 2047u;
         }
-        // after the first passes almost no key still matches the prefix: warps without a match only stream
         const unsigned active = __ballot_sync(0xffffffffu, in);
         if (active == 0u) continue;
         if (in) {
-            // warp-aggregated increment among the lanes that match (early passes put every key in a few bins)
+            // warp-aggregated increment among the lanes that match (the first pass puts every key into a few bins)
             const unsigned grp = __match_any_sync(active, d);
             if ((grp & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(grp));
         }
     }
     __syncthreads();
-    uint32_t* gh = w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS;
+    uint32_t* gh = w.sel_hist + ((size_t)pair * FSEL_PASSES + pass) * SEL_BINS;
     for (int k = threadIdx.x; k < SEL_BINS; k += 256) {
         const uint32_t c = hist[k];
         if (c) atomicAdd(gh + k, c);
+    }
+    // the last CTA of this pair to get here picks the bin that holds rank k
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t ctas = (uint32_t)((n + SEL_TILE - 1) / SEL_TILE);
+        s_last = atomicAdd(w.fsel_done + pair * FSEL_PASSES + pass, 1u) == ctas - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const uint32_t k = pass == 0 ? (uint32_t)(cutoff - 1) : fs->k;
+    uint32_t c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        c[j] = __ldcg(gh + threadIdx.x * 8 + j);
+        gh[threadIdx.x * 8 + j] = 0;      // ready for the next iteration's selection
+        tot += c[j];
+    }
+    uint32_t x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    uint32_t before = x - tot;
+    for (int wv = 0; wv < warp; wv++) before += warp_tot[wv];
+    if (k >= before && k < before + tot) {      // exactly one thread
+        uint32_t kk = k - before;
+        int j = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (j == q && kk >= c[q]) { kk -= c[q]; j = q + 1; }
+        }
+        fs->prefix = (prefix << 11) | (uint32_t)(threadIdx.x * 8 + j);
+        fs->k = kk;
+        fs->all = 0u;
+    }
+    if (threadIdx.x == 0) {
+        w.fsel_done[pair * FSEL_PASSES + pass] = 0u;
+        if (pass == FSEL_PASSES - 1) w.cand_n[pair] = 0u;      // (fsel_moments_kernel fills the list next)
     }
 }
 
@@ -644,14 +719,6 @@ __device__ __forceinline__ void sel_pick_step(IcpWorkspace& w, int pair, int pas
 // multi-CTA histogram passes.
 __device__ __forceinline__ bool sel_is_small(int n_src) { return n_src <= NN_SMALL_PAIR; }
 
-__global__ void __launch_bounds__(1024)
-sel_pick_kernel(IcpWorkspace w, int pass) {
-    const int pair = blockIdx.x;
-    const PairState* st = w.state + pair;
-    if (st->done || sel_is_small(st->n_src)) return;
-    sel_pick_step(w, pair, pass, w.sel_hist + ((size_t)pair * SEL_PASSES + pass) * SEL_BINS);
-}
-
 // The whole selection of a small pair in one launch: one CTA, the six histogram + pick steps back to back on a
 // shared-memory histogram (the keys, at most 256 KB, stay in L1/L2).  For the reference's own cloud sizes the twelve
 // launches of the general path cost more than the search itself.
@@ -686,28 +753,42 @@ __device__ __forceinline__ bool kept(double d2, int i, double tau, int idx_cut) 
     return d2 < tau || (d2 == tau && i <= idx_cut);
 }
 
+// Moments over the kept correspondences, one row per 32 queries.  Small pairs: tau / idx_cut are final (sel_small_kernel).
+// Large pairs: everything below the bracket of the k-th smallest distance is kept and summed here; the bracket's members are
+// listed for fsel_resolve_kernel; everything above is dropped.
 __global__ void __launch_bounds__(NN_THREADS)
 moments_kernel(IcpWorkspace w) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
     __shared__ double T[12];
     __shared__ PairState s;
+    __shared__ FSel fs;
     __shared__ double red[NN_THREADS / 32][16 * 33];
-    if (threadIdx.x == 0) { g = w.grid.params[pair]; s = w.state[pair]; }
+    if (threadIdx.x == 0) { g = w.grid.params[pair]; s = w.state[pair]; fs = w.fsel[pair]; }
     __syncthreads();
     if (threadIdx.x < 12) T[threadIdx.x] = s.T[threadIdx.x];
     __syncthreads();
     if (s.done || blockIdx.x * NN_THREADS >= s.n_src) return;
     const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    const bool small = sel_is_small(s.n_src);
     double m[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) m[k] = 0.0;
+    bool member = false;
     if (i < s.n_src) {
         // the three streams indexed by i are requested together (one memory latency instead of two before the gather)
         const double d2 = w.d2[(size_t)pair * w.max_src + i];
         const int pos = w.nn_pos[(size_t)pair * w.max_src + i];
         const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
-        if (kept(d2, i, s.tau, s.idx_cut)) {
+        bool keep;
+        if (small) {
+            keep = kept(d2, i, s.tau, s.idx_cut);
+        } else {
+            const uint32_t k22 = key32(d2) >> 10;
+            keep = fs.all || k22 < fs.prefix;
+            member = !fs.all && k22 == fs.prefix;
+        }
+        if (keep) {
             const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
             const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
             const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
@@ -716,13 +797,155 @@ moments_kernel(IcpWorkspace w) {
                             b.z - g.shift[2], sqrt(d2));
         }
     }
+    // members of the bracket: one slot each in the pair's list (warp-aggregated)
+    const unsigned mm = __ballot_sync(0xffffffffu, member);
+    if (mm) {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == __ffs(mm) - 1) base = atomicAdd(w.cand_n + pair, (uint32_t)__popc(mm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(mm) - 1);
+        if (member) w.cand_idx[(size_t)pair * w.max_src + base + __popc(mm & ((1u << lane) - 1u))] = i;
+    }
     warp_reduce16_store(m, red[threadIdx.x >> 5],
                         w.partial + ((size_t)pair * w.src_rows + (size_t)(blockIdx.x * (NN_THREADS / 32) + (threadIdx.x >> 5))) * 16);
 }
 
+// The bracket of a large pair (one CTA per pair): its c members ordered by (squared distance, position), the first k' kept.
+// Publishes tau / idx_cut and writes the kept members' moments as row `(n + 31) / 32` of the pair's table.  Up to
+// FSEL_RANKED members (the normal case: a few dozen) every member's rank is counted directly and the kept ones are summed
+// in rank order; a larger bracket (many equal distances) is resolved by bisection on the key bits and summed in position
+// order by a sweep over all queries -- slower, deterministic either way.
+constexpr int SOLVE_THREADS = 512;
+constexpr int FSEL_RANKED = 2048;
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+fsel_resolve_kernel(IcpWorkspace w) {
+    const int pair = blockIdx.x;
+    PairState* st = w.state + pair;
+    const int n = st->n_src;
+    if (st->done) return;
+    __shared__ double sm[SOLVE_THREADS];
+    __shared__ double out16[16];
+    __shared__ unsigned long long s_key[FSEL_RANKED];
+    __shared__ int s_pos[FSEL_RANKED];
+    __shared__ int s_byrank[FSEL_RANKED];
+    __shared__ unsigned long long s_tau;
+    __shared__ int s_cut;
+    double* row = w.partial + ((size_t)pair * w.src_rows + (size_t)((n + 31) / 32)) * 16;
+    const FSel fs = w.fsel[pair];
+    if (sel_is_small(n) || fs.all) {
+        if (threadIdx.x < 16) row[threadIdx.x] = 0.0;
+        if (!sel_is_small(n) && threadIdx.x == 0) { st->tau = CUDART_INF; st->idx_cut = 0x7fffffff; }
+        return;
+    }
+    const int c = (int)w.cand_n[pair];
+    const int kq = (int)fs.k;      // 0-based rank of the k-th smallest distance inside the bracket: members of rank <= kq are kept
+    const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(w.d2 + (size_t)pair * w.max_src);
+    const int32_t* cand = w.cand_idx + (size_t)pair * w.max_src;
+    const GridParams& g = w.grid.params[pair];
+    double m[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) m[k] = 0.0;
+    auto add = [&](int i) {
+        const double d2 = w.d2[(size_t)pair * w.max_src + i];
+        const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
+        const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + w.nn_pos[(size_t)pair * w.max_src + i]);
+        const double qx = st->T[0] * a.x + st->T[1] * a.y + st->T[2] * a.z + st->T[3];
+        const double qy = st->T[4] * a.x + st->T[5] * a.y + st->T[6] * a.z + st->T[7];
+        const double qz = st->T[8] * a.x + st->T[9] * a.y + st->T[10] * a.z + st->T[11];
+        double t[16];
+        accumulate_pair(t, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1], b.z - g.shift[2], sqrt(d2));
+#pragma unroll
+        for (int k = 0; k < 16; k++) m[k] += t[k];
+    };
+    if (c <= FSEL_RANKED) {
+        for (int j = threadIdx.x; j < c; j += SOLVE_THREADS) {
+            const int i = cand[j];
+            s_pos[j] = i;
+            s_key[j] = keys[i];      // non-negative doubles order as their bit patterns
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < c; j += SOLVE_THREADS) {
+            const unsigned long long kj = s_key[j];
+            const int pj = s_pos[j];
+            int rank = 0;
+            for (int u = 0; u < c; u++) rank += (s_key[u] < kj || (s_key[u] == kj && s_pos[u] < pj)) ? 1 : 0;
+            s_byrank[rank] = j;
+            if (rank == kq) { s_tau = kj; s_cut = pj; }
+        }
+        __syncthreads();
+        // kept members in rank order: thread t takes ranks t, t + SOLVE_THREADS, ...
+        for (int r = threadIdx.x; r <= kq && r < c; r += SOLVE_THREADS) add(s_pos[s_byrank[r]]);
+    } else {
+        // bisection on the 64 key bits, then on the 31 position bits among the keys equal to tau; counts by __syncthreads_count
+        unsigned long long tau = 0ull;
+        int need = kq;      // members with a key below the prefix under construction are already accounted for
+        for (int bit = 62; bit >= 0; bit--) {      // (bit 63 is the sign: never set)
+            const unsigned long long probe = tau | (1ull << bit), mask = ~((1ull << bit) - 1ull);
+            int local = 0;
+            for (int j = threadIdx.x; j < c; j += SOLVE_THREADS) {
+                const unsigned long long kj = keys[cand[j]] & mask;
+                local += (kj >= tau && kj < probe) ? 1 : 0;      // keys that have this bit clear under the current prefix
+            }
+            sm[threadIdx.x] = (double)local;
+            __syncthreads();
+            for (int o = SOLVE_THREADS / 2; o > 0; o >>= 1) {
+                if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+                __syncthreads();
+            }
+            const int zeros = (int)sm[0];
+            __syncthreads();
+            if (need >= zeros) { need -= zeros; tau = probe; }
+        }
+        // `need` = rank among the members whose key equals tau, by position
+        int cut = 0;
+        for (int bit = 30; bit >= 0; bit--) {
+            const int probe = cut | (1 << bit), mask = ~((1 << bit) - 1);
+            int local = 0;
+            for (int j = threadIdx.x; j < c; j += SOLVE_THREADS) {
+                const int i = cand[j];
+                local += (keys[i] == tau && (i & mask) >= cut && (i & mask) < probe) ? 1 : 0;
+            }
+            sm[threadIdx.x] = (double)local;
+            __syncthreads();
+            for (int o = SOLVE_THREADS / 2; o > 0; o >>= 1) {
+                if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+                __syncthreads();
+            }
+            const int zeros = (int)sm[0];
+            __syncthreads();
+            if (need >= zeros) { need -= zeros; cut = probe; }
+        }
+        if (threadIdx.x == 0) { s_tau = tau; s_cut = cut; }
+        __syncthreads();
+        // kept members in position order: a sweep over all queries, thread t takes positions t, t + SOLVE_THREADS, ...
+        const uint32_t prefix = fs.prefix;
+        for (int i = threadIdx.x; i < n; i += SOLVE_THREADS) {
+            const unsigned long long ki = keys[i];
+            if ((key32(__longlong_as_double((long long)ki)) >> 10) == prefix && (ki < tau || (ki == tau && i <= cut))) add(i);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->tau = __longlong_as_double((long long)s_tau);
+        st->idx_cut = s_cut;
+    }
+    // fixed-order sum of the threads' partial moments
+    for (int k = 0; k < 16; k++) {
+        sm[threadIdx.x] = m[k];
+        __syncthreads();
+        for (int o = SOLVE_THREADS / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out16[k] = sm[0];
+        __syncthreads();
+    }
+    if (threadIdx.x < 16) row[threadIdx.x] = out16[threadIdx.x];
+}
+
 // ---- solve ---------------------------------------------------------------------------------------------
 // Sum `count` rows of 16 doubles in a fixed order with SOLVE_THREADS threads; result in out16 (shared).
-constexpr int SOLVE_THREADS = 512;
 __device__ __forceinline__ void sum_rows16(const double* __restrict__ rows, int count, double* sm /* [SOLVE_THREADS] */,
                                            double* out16) {
     constexpr int NGRP = SOLVE_THREADS / 16;
@@ -756,7 +979,7 @@ solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     __shared__ double m[16];
     const int n = st->n_src;
     // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32;
+    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32 + 1;      // (+ 1: the bracket row of fsel_resolve_kernel)
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -993,7 +1216,11 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
     R3D_LAUNCH(src_moments_reduce_kernel, P, SOLVE_THREADS, 0, st, w);
     const bool fused = prm.partial_set_size >= 1.0 && !g_force_unfused.load();
     const int want_d2 = (last_dist != nullptr || last_keep != nullptr) ? 1 : 0;
-    if (!fused) R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * SEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
+    if (!fused) {
+        R3D_CUDA(cudaMemsetAsync(w.sel_hist, 0, (size_t)P * FSEL_PASSES * SEL_BINS * sizeof(uint32_t), st));
+        R3D_CUDA(cudaMemsetAsync(w.fsel_done, 0, (size_t)P * FSEL_PASSES * sizeof(uint32_t), st));
+        R3D_CUDA(cudaMemsetAsync(w.fsel, 0, (size_t)P * sizeof(FSel), st));
+    }
     for (int it = 0; it < prm.max_iterations; it++) {
         if (sharded) R3D_CUDA(cudaMemsetAsync(w.partial, 0, shard_doubles * sizeof(double), st));
         {
@@ -1008,12 +1235,11 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
         if (!fused) {
             R3D_LAUNCH(sel_small_kernel, P, 1024, 0, st, w);
             if (w.max_src > NN_SMALL_PAIR) {
-                for (int pass = 0; pass < SEL_PASSES; pass++) {
-                    R3D_LAUNCH(sel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
-                    R3D_LAUNCH(sel_pick_kernel, P, 1024, 0, st, w, pass);
-                }
+                for (int pass = 0; pass < FSEL_PASSES; pass++)
+                    R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
             }
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
+            R3D_LAUNCH(fsel_resolve_kernel, P, SOLVE_THREADS, 0, st, w);
         }
         R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
     }
