@@ -1136,6 +1136,7 @@ struct NnTimer {
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
 static std::atomic<int> g_nn_impl{1};      // 1 = warp-union walk (lean_search.cuh), 2 = tile search (tile_search.cuh)
+extern std::atomic<int> g_k4b_fp32;      // csrc/ransac.cu
 static std::atomic<int> g_force_unfused{0}; // test knob: run partial_set_size == 1 through the select + moments kernels
 
 static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f};
@@ -1395,6 +1396,9 @@ extern "C" int r3d_set_option(int option, double value) {
         case R3D_OPT_GROUP_SEARCH_MAX:
             if (!(value >= 0.0 && value <= 32.0)) return R3D_ERR_INVALID;
             g_group_max.store((int)value);
+            return R3D_OK;
+        case R3D_OPT_K4B_FP32:
+            g_k4b_fp32.store(value != 0.0 ? 1 : 0);
             return R3D_OK;
         case R3D_OPT_FORCE_UNFUSED:
             g_force_unfused.store(value != 0.0 ? 1 : 0);

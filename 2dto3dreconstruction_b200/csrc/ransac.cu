@@ -9,6 +9,7 @@
 //  K4B r3d_ransac3d_score: inlier counts of 4x4 rigid/affine hypotheses over 3-D correspondences.
 // All scoring arithmetic is fp64 so that threshold and truncation decisions match NumPy.
 #include "common.cuh"
+#include <atomic>
 
 namespace r3d {
 
@@ -309,6 +310,166 @@ r3_score_kernel(const double* __restrict__ T, int n_hyp, const Point4* __restric
     if (hyp < n_hyp && cnt) atomicAdd(counts + hyp, cnt);
 }
 
+
+// The same sweep with an fp32 FILTER and an fp64 DECISION (opt-in: R3D_OPT_K4B_FP32; counts identical to the all-fp64 kernel
+// above, which stays the default because it is still the faster one: 5.55 ms against 6.0 ms on BASELINE.json configs[4],
+// profiles/r02_k4b_fp32.md).  The fp64 pipe is the limiter there (78.7 % active, 16 lanes/clk/SMSP); fp32 has twice the
+// lanes and FFMA issues every cycle.  Per tile the CTA converts the staged fp64 records once into fp32
+// (coordinates relative to the tile's first source / target point, which keeps the operands a cloud-extent small) and
+// every lane scores its hypothesis on them: x' = R p' + t' with t' = R o_p + t - o_q folded in fp64 per tile.  The fp32
+// residual r2f differs from the fp64 one by at most `band` (operands rounded to fp32: 2^-24 relative each; three FFMA and
+// a subtraction per coordinate; see r3_band).  r2f < thresh - band counts, r2f > thresh + band does not, and the rare
+// evaluation in between is REDONE with the all-fp64 expression of the kernel above on the original records -- so every
+// count is bit for bit the fp64 kernel's.
+__device__ __forceinline__ float r3_band(float rows_l1_max, float pmax, float tmax, float qmax, float thresh) {
+    // per coordinate: |x'_f - x'| <= u (10 (|R|_1 |p|_inf + |t'|) + 2 |q| + |d|), u = 2^-24 (rounded up to 6.1e-8), |d| <= 2 sqrt(thresh)
+    // in the zone that matters; r2: 2 sqrt(3) |d| e + 3 e^2 + 5 u r2
+    const float d = 2.0f * sqrtf(thresh);
+    const float e = 6.1e-8f * (10.0f * (rows_l1_max * pmax + tmax) + 2.0f * qmax + d);
+    return 1.5f * (3.47f * d * e + 3.0f * e * e + 3.1e-7f * 4.0f * thresh) + 1e-30f;
+}
+
+// the rare evaluation the fp32 filter cannot decide: the fp64 expression of r3_score_kernel on the original records.  Out of
+// line, and reading the hypothesis from memory, so that the hot loop keeps its fp32 operands in registers (inlined, the
+// twelve fp64 coefficients crowd them out and the compiler re-converts them inside the loop).
+__device__ __noinline__ int r3_recheck(const double* __restrict__ t, const double2* sp, const double2* sq, int k, double thresh) {
+    const double2 pxy = sp[2 * k];
+    const double pz = sp[2 * k + 1].x;
+    const double2 qxy = sq[2 * k];
+    const double qz = sq[2 * k + 1].x;
+    const double ex = fma(__ldg(t + 0), pxy.x, fma(__ldg(t + 1), pxy.y, fma(__ldg(t + 2), pz, __ldg(t + 3)))) - qxy.x;
+    const double ey = fma(__ldg(t + 4), pxy.x, fma(__ldg(t + 5), pxy.y, fma(__ldg(t + 6), pz, __ldg(t + 7)))) - qxy.y;
+    const double ez = fma(__ldg(t + 8), pxy.x, fma(__ldg(t + 9), pxy.y, fma(__ldg(t + 10), pz, __ldg(t + 11)))) - qz;
+    return (ex * ex + ey * ey + ez * ez < thresh) ? 1 : 0;
+}
+
+// HPL hypotheses per lane: every staged point is read once (two LDS.128) and scored against HPL hypotheses held in registers
+// -- at one hypothesis per lane the shared-memory pipe, not the FMA pipe, was the limit (ncu: l1tex 79 %, issue 50 %).
+constexpr int RS3_HPL = 2;
+
+__global__ void __launch_bounds__(RS3_THREADS, R3D_RS3_MINB)
+r3_score_f32_kernel(const double* __restrict__ T, int n_hyp, const Point4* __restrict__ P, const Point4* __restrict__ Q,
+                    int n_pts, int pts_per_cta, double thresh, int32_t* __restrict__ counts) {
+    __shared__ __align__(128) double2 sP[2][RS3_TILE * 2];     // raw 32-byte records: (x, y), (z, tag)
+    __shared__ __align__(128) double2 sQ[2][RS3_TILE * 2];
+    __shared__ __align__(16) float4 fP[RS3_TILE], fQ[RS3_TILE];      // the current tile in fp32, relative to its first points
+    __shared__ unsigned s_pmax, s_qmax;                              // max |coordinate| of fP / fQ (float bits)
+    __shared__ __align__(8) unsigned long long bars[2];
+    const double* t[RS3_HPL];
+    float r[RS3_HPL][9], l1[RS3_HPL];
+#pragma unroll
+    for (int h = 0; h < RS3_HPL; h++) {
+        const int hyp = (blockIdx.x * RS3_HPL + h) * RS3_THREADS + threadIdx.x;
+        t[h] = T + (size_t)min(hyp, n_hyp - 1) * 16;      // (lanes past the end score the last hypothesis and drop the result)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) r[h][i * 3 + j] = (float)__ldg(t[h] + i * 4 + j);
+        l1[h] = fmaxf(fmaxf(fabsf(r[h][0]) + fabsf(r[h][1]) + fabsf(r[h][2]), fabsf(r[h][3]) + fabsf(r[h][4]) + fabsf(r[h][5])),
+                      fabsf(r[h][6]) + fabsf(r[h][7]) + fabsf(r[h][8])) * 1.000001f;
+    }
+    const float thr = (float)thresh;
+    const int p0 = blockIdx.y * pts_per_cta, p1 = min(n_pts, p0 + pts_per_cta);
+    const int tiles = (p1 - p0 + RS3_TILE - 1) / RS3_TILE;
+    const uint32_t bar0 = smem_u32(&bars[0]);
+    if (threadIdx.x == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+    }
+    mbar_init_fence();
+    __syncthreads();
+    auto issue = [&](int tile) {      // thread 0 only
+        const int base = p0 + tile * RS3_TILE, m = min(RS3_TILE, p1 - base), b = tile & 1;
+        mbar_arrive_expect_tx(bar0 + 8u * b, 2u * (uint32_t)m * 32u);
+        bulk_copy_g2s(smem_u32(sP[b]), P + base, (uint32_t)m * 32u, bar0 + 8u * b);
+        bulk_copy_g2s(smem_u32(sQ[b]), Q + base, (uint32_t)m * 32u, bar0 + 8u * b);
+    };
+    if (threadIdx.x == 0 && tiles > 0) issue(0);
+    int cnt[RS3_HPL];
+#pragma unroll
+    for (int h = 0; h < RS3_HPL; h++) cnt[h] = 0;
+    unsigned phase = 0;
+    for (int tile = 0; tile < tiles; tile++) {
+        const int b = tile & 1;
+        // buffer b ^ 1 was last read in tile - 1, and every thread has passed the barrier that ended it
+        if (threadIdx.x == 0 && tile + 1 < tiles) issue(tile + 1);
+        if (threadIdx.x == 0) { s_pmax = 0u; s_qmax = 0u; }
+        mbar_wait(bar0 + 8u * b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const int m = min(RS3_TILE, p1 - (p0 + tile * RS3_TILE));
+        const double2* sp = sP[b];
+        const double2* sq = sQ[b];
+        // origins of the tile, and the tile in fp32 (threads 0..m-1: a source point, threads 64..64+m-1: a target point)
+        const double opx = sp[0].x, opy = sp[0].y, opz = sp[1].x, oqx = sq[0].x, oqy = sq[0].y, oqz = sq[1].x;
+        __syncthreads();      // (s_pmax / s_qmax are reset; fP / fQ of the previous tile are no longer read)
+        {
+            const int k = threadIdx.x & (RS3_TILE - 1);
+            const bool src_side = threadIdx.x < RS3_TILE;
+            if (k < m && threadIdx.x < 2 * RS3_TILE) {
+                const double2* rec = src_side ? sp : sq;
+                const float x = (float)(rec[2 * k].x - (src_side ? opx : oqx)), y = (float)(rec[2 * k].y - (src_side ? opy : oqy)),
+                            z = (float)(rec[2 * k + 1].x - (src_side ? opz : oqz));
+                (src_side ? fP : fQ)[k] = make_float4(x, y, z, 0.0f);
+                const unsigned mx = __reduce_max_sync(__activemask(), __float_as_uint(fmaxf(fmaxf(fabsf(x), fabsf(y)), fabsf(z))));
+                if ((threadIdx.x & 31) == 0 || k == 0) atomicMax(src_side ? &s_pmax : &s_qmax, mx);
+            } else if (threadIdx.x < 2 * RS3_TILE) {
+                // past the end of the last tile: a pair infinitely far apart (never counted, never undecided)
+                (src_side ? fP : fQ)[k] = src_side ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(3.0e19f, 3.0e19f, 3.0e19f, 0.0f);
+            }
+        }
+        __syncthreads();
+        // t' = R o_p + t - o_q in fp64, then fp32; the band of this tile
+        float tx[RS3_HPL], ty[RS3_HPL], tz[RS3_HPL], lo[RS3_HPL], hi[RS3_HPL];
+#pragma unroll
+        for (int h = 0; h < RS3_HPL; h++) {
+            const double* th = t[h];
+            tx[h] = (float)(fma(__ldg(th + 0), opx, fma(__ldg(th + 1), opy, fma(__ldg(th + 2), opz, __ldg(th + 3)))) - oqx);
+            ty[h] = (float)(fma(__ldg(th + 4), opx, fma(__ldg(th + 5), opy, fma(__ldg(th + 6), opz, __ldg(th + 7)))) - oqy);
+            tz[h] = (float)(fma(__ldg(th + 8), opx, fma(__ldg(th + 9), opy, fma(__ldg(th + 10), opz, __ldg(th + 11)))) - oqz);
+            const float band = r3_band(l1[h], __uint_as_float(s_pmax), fmaxf(fmaxf(fabsf(tx[h]), fabsf(ty[h])), fabsf(tz[h])) * 1.000001f,
+                                       __uint_as_float(s_qmax), thr);
+            lo[h] = thr - band;
+            hi[h] = thr + band;
+        }
+        // 32 points without a branch (undecided evaluations are remembered as bits), then the rare rechecks
+#pragma unroll 1
+        for (int kb = 0; kb < RS3_TILE; kb += 32) {
+            unsigned undecided[RS3_HPL];
+#pragma unroll
+            for (int h = 0; h < RS3_HPL; h++) undecided[h] = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float4 p = fP[kb + j], q = fQ[kb + j];
+#pragma unroll
+                for (int h = 0; h < RS3_HPL; h++) {
+                    const float dx = fmaf(r[h][0], p.x, fmaf(r[h][1], p.y, fmaf(r[h][2], p.z, tx[h]))) - q.x;
+                    const float dy = fmaf(r[h][3], p.x, fmaf(r[h][4], p.y, fmaf(r[h][5], p.z, ty[h]))) - q.y;
+                    const float dz = fmaf(r[h][6], p.x, fmaf(r[h][7], p.y, fmaf(r[h][8], p.z, tz[h]))) - q.z;
+                    const float r2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    cnt[h] += (r2f < lo[h]);
+                    undecided[h] |= (r2f >= lo[h] && r2f <= hi[h]) ? (1u << j) : 0u;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < RS3_HPL; h++) {
+                while (undecided[h]) {
+                    const int j = __ffs(undecided[h]) - 1;
+                    undecided[h] &= undecided[h] - 1u;
+                    cnt[h] += r3_recheck(t[h], sp, sq, kb + j, thresh);
+                }
+            }
+        }
+        __syncthreads();      // the buffers may be refilled
+    }
+#pragma unroll
+    for (int h = 0; h < RS3_HPL; h++) {
+        const int hyp = (blockIdx.x * RS3_HPL + h) * RS3_THREADS + threadIdx.x;
+        if (hyp < n_hyp && cnt[h]) atomicAdd(counts + hyp, cnt[h]);
+    }
+}
+
+std::atomic<int> g_k4b_fp32{0};
+
 }  // namespace r3d
 
 using namespace r3d;
@@ -368,8 +529,13 @@ extern "C" int r3d_ransac3d_score(const double* T, int n_hyp, const double* P, c
     int per = (n_pts + gy - 1) / gy;
     per = (per + RS3_TILE - 1) / RS3_TILE * RS3_TILE;
     gy = (n_pts + per - 1) / per;
-    R3D_LAUNCH(r3_score_kernel, dim3(gx, gy), RS3_THREADS, 0, st, T, n_hyp, (const Point4*)P, (const Point4*)Q, n_pts, per,
-               thresh, counts_out);
+    // non-finite or huge thresholds / hypotheses: the fp32 filter has nothing to offer, and NaN needs the fp64 comparison
+    if (!g_k4b_fp32.load() || !(thresh > 1e-30 && thresh < 1e30))
+        R3D_LAUNCH(r3_score_kernel, dim3(gx, gy), RS3_THREADS, 0, st, T, n_hyp, (const Point4*)P, (const Point4*)Q, n_pts, per,
+                   thresh, counts_out);
+    else
+        R3D_LAUNCH(r3_score_f32_kernel, dim3((gx + RS3_HPL - 1) / RS3_HPL, gy), RS3_THREADS, 0, st, T, n_hyp, (const Point4*)P,
+                   (const Point4*)Q, n_pts, per, thresh, counts_out);
     return R3D_OK;
 }
 

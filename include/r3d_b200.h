@@ -276,10 +276,12 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
  *                          a multiple of 0 disables the skipping of searches that cannot change the neighbour
  *   R3D_OPT_GROUP_SEARCH_MAX  0..32 (default 12): seeded tasks of the ICP loop in which at most this many of the 32 lanes still
  *                          search are served by csrc/lean_search.cuh group_search (eight lanes per query, only that query's
- *                          own cells) instead of the warp-union walk; 0 = always the union walk */
+ *                          own cells) instead of the warp-union walk; 0 = always the union walk
+ *   R3D_OPT_K4B_FP32       non-zero: r3d_ransac3d_score filters in fp32 and redoes the residual in fp64 inside the rounding band
+ *                          (same counts as the default all-fp64 kernel; measured slower, kept as the cross-check) */
 typedef enum {
     R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5, R3D_OPT_FORCE_UNFUSED = 6,
-    R3D_OPT_GROUP_SEARCH_MAX = 7
+    R3D_OPT_GROUP_SEARCH_MAX = 7, R3D_OPT_K4B_FP32 = 8
 } r3d_option;
 int r3d_set_option(int option, double value);
 

@@ -227,3 +227,39 @@ def test_k4b_against_the_reference_golden():
         # device-generated hypotheses near T* find (almost) the same consensus set; the bulk scores 0-2 inliers either way
         dev_counts = ops.ransac3d_score(Td, Pd, Qd).cpu().numpy()
         assert (np.abs(dev_counts[ok] - want[ok]) <= np.maximum(2, want[ok] // 50)).all()
+
+
+def test_ransac3d_fp32_filter_equals_the_fp64_kernel():
+    """r3d_ransac3d_score's opt-in kernel (R3D_OPT_K4B_FP32) filters in fp32 and decides in fp64 inside the rounding band; its
+    counts must be bit for bit those of the default all-fp64 kernel -- also when MOST residuals sit at the threshold (hypotheses
+    within 1e-3 of the true motion, threshold = the median residual), far from the origin, and for scaled / degenerate
+    hypotheses."""
+    import torch
+    ops = sub("ops")
+    L = sub("_capi").lib()
+    rng = np.random.default_rng(4)
+    n = 30000
+    for offset, spread in ((0.0, 1000.0), (5.0e4, 300.0), (0.0, 3.0)):
+        P = rng.uniform(-spread, spread, (n, 3)) + offset
+        ang = 0.1
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+        T[:3, 3] = [3.0, -2.0, 1.0]
+        Q = O.get_transformed_points(P, T) + rng.normal(size=(n, 3)) * np.sqrt(10.0 / 3.0)      # E[r2] = 10: the threshold
+        hyps = np.tile(T, (600, 1, 1))
+        hyps[:, :3, 3] += rng.normal(size=(600, 3)) * 1e-3
+        hyps[:200, :3, :3] += rng.normal(size=(200, 3, 3)) * 1e-6
+        hyps[590:] = np.eye(4) * np.array([1, 1, 1, 1.0])[None, :, None] * rng.uniform(0.5, 2.0, size=(10, 1, 1))
+        hyps[599] = 0.0
+        Pd, Qd = ops.pack_xyzw(torch.from_numpy(P).cuda()), ops.pack_xyzw(torch.from_numpy(Q).cuda())
+        Hd = torch.from_numpy(hyps).cuda()
+        for thresh in (10.0, 2.5, 400.0):
+            want = ops.ransac3d_score(Hd, Pd, Qd, thresh=thresh).cpu().numpy()
+            try:
+                assert L.r3d_set_option(8, 1.0) == 0
+                got = ops.ransac3d_score(Hd, Pd, Qd, thresh=thresh).cpu().numpy()
+            finally:
+                L.r3d_set_option(8, 0.0)
+            assert np.array_equal(got, want), (offset, spread, thresh, int((got != want).sum()))
+            if thresh == 10.0:
+                assert 0.2 * n < want[0] < 0.9 * n      # the threshold cuts through the bulk of the residuals

@@ -157,27 +157,47 @@ def run(sections=None, icp_partials=(1.0, 0.7)):
         out["K3c_affine_fit"] = {"what": "homo_rigid_transform_3d on 2 M pairs", "ms": ms, "algorithmic_bytes": 48 * n,
                                  "achieved_gbs": 48 * n / ms / 1e6, "frac_of_hbm": 48 * n / ms / 1e6 / HBM}
 
-    # ---- K4B: 100k hypotheses x 50k correspondences (configs[4]) ----------------------------------------------------
+    # ---- K4B: 100k hypotheses x 50k correspondences (configs[4]), inputs of SURVEY.md 8(d) C5 ------------------------------
     if "k4b" in want:
         nh, npnt = 100_000, 50_000
-        Pp = torch.zeros((npnt, 4), dtype=torch.float64, device=dev)
-        Pp[:, :3] = (torch.rand((npnt, 3), dtype=torch.float64, device=dev, generator=g) * 2000 - 1000)
-        Qp = Pp.clone()
-        Qp[:, :3] += torch.randn((npnt, 3), dtype=torch.float64, device=dev, generator=g)
-        Hy = torch.eye(4, dtype=torch.float64, device=dev).repeat(nh, 1, 1).contiguous()
-        Hy[:, :3, 3] = torch.randn((nh, 3), dtype=torch.float64, device=dev, generator=g)
-        cnt = torch.empty(nh, dtype=torch.int32, device=dev)
+        rng5 = np.random.default_rng(11)
+        P5 = rng5.uniform(-1000, 1000, (npnt, 3)).astype(np.float32).astype(np.float64)
+        ang5 = np.deg2rad(2.0)
+        R5 = np.array([[np.cos(ang5), -np.sin(ang5), 0], [np.sin(ang5), np.cos(ang5), 0], [0, 0, 1]])
+        Q5 = P5 @ R5.T + np.array([15.0, -8.0, 5.0]) + rng5.normal(size=(npnt, 3))
+        outl = rng5.random(npnt) < 0.4
+        Q5[outl] = rng5.uniform(-1000, 1000, (int(outl.sum()), 3))
+        Pp = ops.pack_xyzw(torch.from_numpy(P5).to(dev))
+        Qp = ops.pack_xyzw(torch.from_numpy(Q5).to(dev))
+        rs5 = np.random.RandomState(12345)
+        entry = {"what": "SURVEY 8(d) C5: 50k correspondences (60 % inliers of a rigid motion + N(0,1), 40 % outliers), 100k hypotheses from "
+                         "random minimal samples generated on the device (K6), threshold 10", "fp64_instructions_per_evaluation": 16}
+        for kind, k in (("rigid", 3), ("affine", 4)):
+            samples = torch.from_numpy(rs5.randint(npnt, size=(nh, k)).astype(np.int32)).to(dev)
+            Hy, status = ops.hypotheses_3d(Pp, Qp, samples, kind)
+            Hy = Hy.contiguous()
+            cnt = torch.empty(nh, dtype=torch.int32, device=dev)
 
-        def k4b():
-            C.check(L.r3d_ransac3d_score(C.ptr(Hy), nh, C.ptr(Pp), C.ptr(Qp), npnt, 10.0, C.ptr(cnt), st))
+            def k4b():
+                C.check(L.r3d_ransac3d_score(C.ptr(Hy), nh, C.ptr(Pp), C.ptr(Qp), npnt, 10.0, C.ptr(cnt), st))
 
-        ms = timed(k4b, flush=False)
-        ev = nh * npnt
-        out["K4B_ransac3d_sweep"] = {"what": "100k rigid/affine 4x4 hypotheses x 50k correspondences, fp64", "ms": ms,
-                                     "evaluations_per_s": ev / ms * 1e3, "fp64_instructions_per_evaluation": 16,
-                                     "fp64_warp_instr_per_s": 16 * ev / 32 / ms * 1e3,
-                                     "frac_of_fp64_pipe": 16 * ev / 32 / ms * 1e3 / (592 * 1.965e9 / 2),
-                                     "note": "9 DFMA + 3 DADD + 3 (r2) + 1 compare per evaluation; pipe peak = 16 lanes/clk/SMSP x 592 SMSPs"}
+            ms = timed(k4b, flush=False)
+            ref_counts = cnt.clone()
+            L.r3d_set_option(8, 1.0)
+            ms32 = timed(k4b, flush=False)
+            L.r3d_set_option(8, 0.0)
+            ev = nh * npnt
+            entry[kind] = {"ms": ms, "evaluations_per_s": ev / ms * 1e3, "frac_of_fp64_pipe": 16 * ev / 32 / ms * 1e3 / (592 * 1.965e9 / 2),
+                           "ms_fp32_filter_kernel": ms32, "evaluations_per_s_fp32_filter_kernel": ev / ms32 * 1e3,
+                           "counts_equal": bool(torch.equal(ref_counts, cnt)), "best_inlier_count": int(ref_counts.max().item()),
+                           "degenerate_samples": int((status != 0).sum().item())}
+        entry["ms"] = entry["rigid"]["ms"]
+        entry["evaluations_per_s"] = entry["rigid"]["evaluations_per_s"]
+        entry["frac_of_fp64_pipe"] = entry["rigid"]["frac_of_fp64_pipe"]
+        entry["note"] = ("default kernel: all fp64, 9 DFMA + 3 DADD + 3 (r2) + 1 compare per evaluation, pipe peak = 16 lanes/clk/SMSP x 592 SMSPs; "
+                         "opt-in kernel (R3D_OPT_K4B_FP32): fp32 filter, two hypotheses per lane, the fp64 expression redone inside the rounding "
+                         "band -- identical counts, measured slower (profiles/r02_k4b_fp32.md)")
+        out["K4B_ransac3d_sweep"] = entry
 
     # ---- K4A: reference-exact 2-D scoring at its native size (100 hypotheses x 1100 keypoints) ---------------------
     if "k4a" in want:
