@@ -285,7 +285,6 @@ gather_kernel(GridWorkspace w, const Point4* __restrict__ dst, const int32_t* __
     const uint32_t* keys = sorted_keys(w, g, pair);
     const uint32_t* vals = w.vals[g.n_passes & 1] + (size_t)pair * w.max_dst;
     Point4* out = w.sorted + (size_t)pair * w.max_dst;
-    float4* packed = w.packed + (size_t)pair * w.max_dst;
     const Point4* src = dst + dst_off[pair];
     uint32_t starts = 0;
 #pragma unroll
@@ -299,12 +298,6 @@ gather_kernel(GridWorkspace w, const Point4* __restrict__ dst, const int32_t* __
             store_point_tagged(out + i, p.x, p.y, p.z, (int32_t)v, (int32_t)i);
             const uint32_t k = keys[i];
             starts += (i == 0) || ((keys[i - 1] >> 6) != (k >> 6));
-            // fp32 copy relative to the block's origin (tile_search.cuh stages these records by bulk copy)
-            const uint32_t blk = k >> 6;
-            const int cbx = (int)(blk % (uint32_t)g.bx), cby = (int)((blk / (uint32_t)g.bx) % (uint32_t)g.by),
-                      cbz = (int)(blk / ((uint32_t)g.bx * (uint32_t)g.by));
-            packed[i] = make_float4((float)(p.x - block_origin(g.ox, 4 * cbx, g.cell)), (float)(p.y - block_origin(g.oy, 4 * cby, g.cell)),
-                                    (float)(p.z - block_origin(g.oz, 4 * cbz, g.cell)), __int_as_float((int)v));
         }
     }
     starts = __reduce_add_sync(0xffffffffu, starts);
@@ -430,21 +423,27 @@ blocks_assign_kernel(GridWorkspace w) {
     }
 }
 
-// one warp per block: the 64 cell starts are lower bounds of (block<<6 | f) in the block's key range
+// one warp per block: the 64 cell starts are lower bounds of (block<<6 | f) in the block's key range.  Stored compactly:
+// a 64-bit occupancy mask per block, and the starts of the OCCUPIED cells only, in cell order, at cell_first[first ..
+// first + n_occ) where first = the block's first sorted position (a block has at least as many points as occupied cells,
+// so the block's own range of positions has room for them), followed by the end of the block -- explicitly when the range
+// has a free slot, else it is the next block's first entry (= this block's end) or the global sentinel at n_pts.
 __global__ void __launch_bounds__(GB_THREADS)
 cell_table_kernel(GridWorkspace w) {
     const int pair = blockIdx.y;
     const GridParams* gp = w.params + pair;
     const int n_blocks = gp->n_blocks;
     const int lane = threadIdx.x & 31;
-    uint32_t* cs = w.cell_start + (size_t)pair * ((size_t)64 * w.max_dst + 64);
-    if (blockIdx.x == 0 && threadIdx.x == 0) cs[(size_t)64 * n_blocks] = (uint32_t)gp->n_pts;   // global sentinel
+    uint4* info = w.block_info + (size_t)pair * w.max_dst;
+    uint32_t* cf = w.cell_first + (size_t)pair * (w.max_dst + 1);
+    if (blockIdx.x == 0 && threadIdx.x == 0) cf[gp->n_pts] = (uint32_t)gp->n_pts;   // global sentinel
     const uint32_t* keys = w.keys[gp->n_passes & 1] + (size_t)pair * w.max_dst;
     const uint32_t* bf = w.block_first + (size_t)pair * (w.max_dst + 1);
     const int warps = gridDim.x * (GB_THREADS / 32);
     for (int b = blockIdx.x * (GB_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
         const uint32_t first = bf[b], last = bf[b + 1];
         const uint32_t blk = w.block_key[(size_t)pair * w.max_dst + b];
+        uint32_t start[2], next[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t f = (uint32_t)(lane + 32 * h);
@@ -454,7 +453,22 @@ cell_table_kernel(GridWorkspace w) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (keys[mid] < target) lo = mid + 1; else hi = mid;
             }
-            cs[(size_t)64 * b + f] = lo;
+            start[h] = lo;
+        }
+        // a cell is occupied iff the next cell starts later
+        next[0] = __shfl_down_sync(0xffffffffu, start[0], 1);
+        const uint32_t s32 = __shfl_sync(0xffffffffu, start[1], 0);
+        if (lane == 31) next[0] = s32;
+        next[1] = __shfl_down_sync(0xffffffffu, start[1], 1);
+        if (lane == 31) next[1] = last;
+        const unsigned m0 = __ballot_sync(0xffffffffu, next[0] > start[0]), m1 = __ballot_sync(0xffffffffu, next[1] > start[1]);
+        const unsigned below = (1u << lane) - 1u;
+        if ((m0 >> lane) & 1u) cf[first + __popc(m0 & below)] = start[0];
+        if ((m1 >> lane) & 1u) cf[first + __popc(m0) + __popc(m1 & below)] = start[1];
+        if (lane == 0) {
+            const uint32_t n_occ = (uint32_t)(__popc(m0) + __popc(m1));
+            if (first + n_occ < last) cf[first + n_occ] = last;
+            info[b] = make_uint4(m0, m1, first, last);
         }
     }
 }
@@ -482,7 +496,7 @@ size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_ds
     w.max_dst = max_dst;
     w.tiles = (max_dst + RS_TILE - 1) / RS_TILE;
     size_t slots = 64;
-    while (slots < 4 * (size_t)max_dst) slots <<= 1;
+    while (slots < (size_t)max_dst + (size_t)max_dst / 2) slots <<= 1;      // load factor <= 2/3 even if every point had its own block
     w.hash_slots = slots;
     const size_t P = (size_t)n_pairs, M = (size_t)max_dst;
     w.bbox = a.take<unsigned long long>(P * 6);
@@ -494,12 +508,12 @@ size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_ds
     w.vals[1] = a.take<uint32_t>(P * M);
     w.hist = a.take<uint32_t>(P * 256 * w.tiles);
     w.sorted = a.take<Point4>(P * M);
-    w.packed = a.take<float4>(P * M);
     w.tile_cnt = a.take<uint32_t>(P * w.tiles);
     w.hash = a.take<uint2>(P * slots);
     w.block_key = a.take<uint32_t>(P * M);
     w.block_first = a.take<uint32_t>(P * (M + 1));
-    w.cell_start = a.take<uint32_t>(P * (64 * M + 64));
+    w.block_info = a.take<uint4>(P * M);
+    w.cell_first = a.take<uint32_t>(P * (M + 1));
     return a.used;
 }
 

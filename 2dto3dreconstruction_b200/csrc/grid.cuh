@@ -8,14 +8,13 @@
 //   - points are radix-sorted by key = (block_linear << 6) | (fz<<4 | fy<<2 | fx), stable, so
 //     every fine cell, every x-run of fine cells inside a block, and every block is ONE
 //     contiguous range of the sorted array, and points inside a cell keep ascending cloud index
-//   - cell_start[b*64 + f] = first sorted position of cell f of block b (lower bound, so empty
-//     cells have start == next start and the end of cell f is cell_start[b*64 + f + 1])
-//   - packed[i] = the sorted point i once more as 16 bytes: fp32 coordinates RELATIVE TO ITS BLOCK'S
-//     ORIGIN (|value| <= 4 cells, so the rounding is 2^-24 of a few cells) + the cloud index.  A block,
-//     or any run of its cells, is one contiguous range of `packed`: the unit the tile search stages
-//     into shared memory with one bulk copy (tile_search.cuh)
+//   - block_info[b] = {occupancy mask of the block's 64 cells (2 x 32 bits), first sorted position, end};
+//     cell_first[first + j] = first sorted position of the block's j-th OCCUPIED cell (in cell order), and the
+//     entry after the last occupied cell is the end of the block: the points of cells [f0, f1) of block b are the
+//     range cell_first[first + popc(mask below f0)] .. cell_first[first + popc(mask below f1)]   (cell_range below;
+//     a dense 64-entry table per block was 79 MB per 640x480 pair, this is 6 MB, and an empty run costs no load)
 //
-// Search contract (lean_search.cuh, tile_search.cuh): given an upper bound that is the distance to an
+// Search contract (lean_search.cuh): given an upper bound that is the distance to an
 // actual point of the cloud, every cell that intersects the ball of that radius around the query is
 // visited and the lexicographic minimum of (squared distance, cloud index) is returned.  Every point
 // closer than the bound lies in that ball, so the result is the exact nearest neighbour with
@@ -50,9 +49,9 @@ struct SortDesc {             // per pair: how many keys, how many 8-bit radix p
 
 struct GridView {             // raw pointers of one pair's grid
     const Point4* pts;        // sorted points (idx = position in the original cloud)
-    const float4* packed;     // sorted points, fp32 relative to their block's origin, w = cloud index bits
     const uint2* hash;        // {block_linear, block_id}
-    const uint32_t* cell_start;
+    const uint4* block_info;
+    const uint32_t* cell_first;
     const uint32_t* block_key;    // block_id -> block_linear
     const uint32_t* block_first;  // block_id -> first sorted position (n_blocks + 1 entries)
 };
@@ -74,6 +73,22 @@ __device__ __forceinline__ int find_block(const uint2* __restrict__ hash, uint32
         if (e.x == key) return (int)e.y;
         if (e.x == HASH_EMPTY) return -1;
         s = (s + 1) & mask;
+    }
+}
+
+// Sorted range [s, s + cnt) of the points in cells [f0, f1) (0 <= f0 < f1 <= 64, fine-cell numbers z<<4 | y<<2 | x) of block b.
+__device__ __forceinline__ void cell_range(const GridView& v, int b, int f0, int f1, uint32_t& s, uint32_t& cnt) {
+    const uint4 bi = __ldg(v.block_info + b);
+    const unsigned long long mask = ((unsigned long long)bi.y << 32) | (unsigned long long)bi.x;
+    const unsigned long long below0 = mask & ((1ull << f0) - 1ull);
+    const unsigned long long below1 = f1 >= 64 ? mask : (mask & ((1ull << f1) - 1ull));
+    const int j0 = __popcll(below0), j1 = __popcll(below1);
+    s = 0;
+    cnt = 0;
+    if (j1 > j0) {
+        const uint32_t* cf = v.cell_first + bi.z;
+        s = __ldg(cf + j0);
+        cnt = __ldg(cf + j1) - s;
     }
 }
 
@@ -124,12 +139,12 @@ struct GridWorkspace {
     uint32_t* vals[2];
     uint32_t* hist;                 // [pair][256][tiles]
     Point4* sorted;                 // [pair][max_dst]
-    float4* packed;                 // [pair][max_dst]
     uint32_t* tile_cnt;             // [pair][tiles] block-start counts per tile
     uint2* hash;                    // [pair][hash_slots]
     uint32_t* block_key;            // [pair][max_dst]
     uint32_t* block_first;          // [pair][max_dst + 1]
-    uint32_t* cell_start;           // [pair][64 * max_dst + 64]
+    uint4* block_info;              // [pair][max_dst]
+    uint32_t* cell_first;           // [pair][max_dst + 1]
 };
 
 size_t grid_workspace_layout(GridWorkspace& w, Arena& a, int n_pairs, int max_dst);
@@ -143,9 +158,9 @@ int grid_build(const GridWorkspace& w, const Point4* dst, const int32_t* dst_off
 __device__ __forceinline__ GridView grid_view(const GridWorkspace& w, int pair) {
     GridView v;
     v.pts = w.sorted + (size_t)pair * w.max_dst;
-    v.packed = w.packed + (size_t)pair * w.max_dst;
     v.hash = w.hash + (size_t)pair * w.hash_slots;
-    v.cell_start = w.cell_start + (size_t)pair * ((size_t)64 * w.max_dst + 64);
+    v.block_info = w.block_info + (size_t)pair * w.max_dst;
+    v.cell_first = w.cell_first + (size_t)pair * (w.max_dst + 1);
     v.block_key = w.block_key + (size_t)pair * w.max_dst;
     v.block_first = w.block_first + (size_t)pair * (w.max_dst + 1);
     return v;

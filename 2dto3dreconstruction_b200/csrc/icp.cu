@@ -2,9 +2,9 @@
 //
 // Per iteration (no host round trip; converged pairs turn into early-exit CTAs):
 //   nn_query_kernel  q = T_cum * a (fp64), exact NN on the sparse-block grid, one warp per 32
-//                    spatially adjacent queries (tile_search.cuh: blocks staged into shared memory
-//                    by TMA, per-lane walk, fp32 filter + fp64 decision; the source cloud is sorted
-//                    by cell key once, before the loop).  Iterations >= 2 seed the upper bound with
+//                    spatially adjacent queries (lean_search.cuh: warp-union walk, and a group search
+//                    for tasks with few searching lanes; the source cloud is sorted by cell key
+//                    once, before the loop).  Iterations >= 2 seed the upper bound with
 //                    the previous neighbour and skip the search altogether when the neighbour
 //                    provably cannot change.  With partial_set_size == 1 the 16 Kabsch moments are
 //                    reduced in the same kernel.
@@ -15,20 +15,16 @@
 //                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126)
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
-#include "tile_search.cuh"
+#include "lean_search.cuh"
 #include <mutex>
 #include <vector>
 
 namespace r3d {
 
 constexpr int NN_THREADS = 128;
-// resident CTAs per SM the kernel is compiled for: the lean search is latency bound and wants 8 (64 registers);
-// the tile search holds ~8.6 KB of staging per warp
+// resident CTAs per SM the kernel is compiled for: the search is latency bound and wants 8 (64 registers)
 #ifndef R3D_LEAN_MIN_CTAS
 #define R3D_LEAN_MIN_CTAS 8
-#endif
-#ifndef R3D_TILE_MIN_CTAS
-#define R3D_TILE_MIN_CTAS 5
 #endif
 // partial-set selection (radix select, below): passes x bins of the per-pair histograms in the workspace
 constexpr int SEL_PASSES = 6;
@@ -296,8 +292,8 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
 // out dynamically, and each physical warp runs some of them back to back.  The moment sums are kept per VIRTUAL
 // warp, so their summation order -- and therefore every bit of the result -- does not depend on how many CTAs
 // this launch happened to get (chunk size, number of pairs in flight, GPU count).
-// IMPL selects the search: 1 = lean_search.cuh (warp-union walk, the default), 2 = tile_search.cuh (blocks staged
-// by TMA, per-lane walk, fp32 filter + fp64 decision).  Both are exact, so every output bit is the same under either.
+// IMPL = 1: the search of lean_search.cuh (a second, TMA-staged tile search lived here in round 2; it was exact and slower,
+// profiles/r02_nn_tile_search.md, and is gone again).
 //
 // Skipping searches that cannot change the answer.  When a seeded search ends with the seed p still the
 // nearest point, it also knows a lower bound L2 of the distance to every OTHER point (the runner-up among
@@ -314,6 +310,7 @@ struct LeanTuning {
     float slack_mult;        // slack = slack_mult * (movement of the query in this iteration) ...
     float slack_max_frac;    // ... if that is at most slack_max_frac * cell (else 0: still moving too fast to bother)
     int group_max;           // tasks with at most this many searching lanes go through group_search (0 = never)
+    int slack_clamp;         // a query that moves faster than that still asks for slack_max_frac * cell (else for nothing extra)
 };
 
 #ifndef R3D_NN_PREFETCH
@@ -323,10 +320,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 
 template <int IMPL> struct SearchSmem;
 template <> struct SearchSmem<1> { double2 list[LEAN_WARP_SMEM]; };      // survivors list; never shared with the reduction: its stale slots must stay real points
-template <> struct SearchSmem<2> { TileWarp tile; };
 
 template <int IMPL, bool SEEDED, bool FUSED>
-__global__ void __launch_bounds__(NN_THREADS, IMPL == 2 ? R3D_TILE_MIN_CTAS : R3D_LEAN_MIN_CTAS)
+__global__ void __launch_bounds__(NN_THREADS, R3D_LEAN_MIN_CTAS)
 nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
@@ -371,10 +367,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         mbar_init_fence();
         __syncwarp();
 #endif
-    } else {
-        if (lane == 0) mbar_init(smem_u32(&ssm[warp].tile.mbar), 1);
-        mbar_init_fence();
-        __syncwarp();
     }
     while (true) {
         int vw = 0;
@@ -406,7 +398,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             Best seed, other;
             seed.d2 = CUDART_INF; seed.idx = 0x7fffffff; seed.pos = -1;
             other.d2 = CUDART_INF; other.idx = 0x7fffffff; other.pos = -1;
-            double sbx = 0.0, sby = 0.0, sbz = 0.0;      // coordinates of the seed
             float left = 0.0f, slack = 0.0f;      // bound on the other points left after this iteration's movement
             bool skip = false;
             if (active) {
@@ -415,9 +406,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
                 qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
                 if (SEEDED) {
-                    // (the tile kernel has registers to keep the seed's coordinates for the moment sums; the lean one, at 64, reloads)
-                    if constexpr (IMPL == 2) consider_xyz(seed, sbx, sby, sbz, v.pts, nn_pos[i], qx, qy, qz);
-                    else consider(seed, v.pts, nn_pos[i], qx, qy, qz);
+                    consider(seed, v.pts, nn_pos[i], qx, qy, qz);      // (at 64 registers the seed's coordinates are reloaded for the moment sums)
                     const double mx = D[0] * a.x + D[1] * a.y + D[2] * a.z + D[3];
                     const double my = D[4] * a.x + D[5] * a.y + D[6] * a.z + D[7];
                     const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
@@ -428,7 +417,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     left = __fsub_rd(budget[i], moved);
                     skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
                     const float want = moved * tune.slack_mult;
-                    slack = (want <= slack_max) ? want + 1e-4f * slack_max : 0.0f;
+                    slack = (want <= slack_max) ? want + 1e-4f * slack_max : (tune.slack_clamp ? slack_max : 0.0f);
                 }
             }
             R3D_STAT(0, 1);
@@ -448,11 +437,6 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     if ((walk_m >> lane) & 1u) cover = cover_w;
                 }
                 lb_other = sqrtf(__double2float_rd(other.d2));
-            } else {
-                // (the range queue shares the warp's reduction scratch: the two are never live at the same time)
-                static_assert(sizeof(scratch[0]) >= TILE_QUEUE_WORDS * sizeof(uint32_t), "the range queue lives in the reduction scratch");
-                tile_search(ssm[warp].tile, reinterpret_cast<uint32_t*>(scratch[warp]), phase, seed, other, lb_other, v, g, active && !skip,
-                            qx, qy, qz, slack, cover, qpt);
             }
             const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
 #ifdef R3D_NN_STATS
@@ -484,13 +468,9 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
 #pragma unroll
                 for (int k = 0; k < 16; k++) m[k] = 0.0;
                 if (active && primary) {
-                    double bx = sbx, by = sby, bz = sbz;
-                    if (IMPL != 2 || !seed_wins) {
-                        const Point4 b = load_point(v.pts + best.pos);
-                        bx = b.x; by = b.y; bz = b.z;
-                    }
-                    accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], bx - g.shift[0], by - g.shift[1],
-                                    bz - g.shift[2], sqrt(best.d2));
+                    const Point4 b = load_point(v.pts + best.pos);
+                    accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
+                                    b.z - g.shift[2], sqrt(best.d2));
                 }
                 acc += warp_reduce16_small(m, scratch[warp]);
             }
@@ -1135,11 +1115,12 @@ struct NnTimer {
 };
 
 // ---- host orchestration -----------------------------------------------------------------------------------------
-static std::atomic<int> g_nn_impl{1};      // 1 = warp-union walk (lean_search.cuh), 2 = tile search (tile_search.cuh)
+static std::atomic<int> g_nn_impl{1};      // 1 = the search of lean_search.cuh (the only one left; the option is kept for ABI stability)
 extern std::atomic<int> g_k4b_fp32;      // csrc/ransac.cu
 static std::atomic<int> g_force_unfused{0}; // test knob: run partial_set_size == 1 through the select + moments kernels
 
 static std::atomic<float> g_slack_mult{8.0f}, g_slack_max_frac{0.25f};
+static std::atomic<int> g_slack_clamp{0};
 static std::atomic<int> g_group_max{12};      // group_search for tasks with at most this many searching lanes (results do not depend on it)
 
 template <int IMPL>
@@ -1148,6 +1129,7 @@ static int launch_query(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int
     tune.slack_mult = g_slack_mult.load();
     tune.slack_max_frac = g_slack_max_frac.load();
     tune.group_max = g_group_max.load();
+    tune.slack_clamp = g_slack_clamp.load();
     if (seeded) {
         if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
         else R3D_LAUNCH((nn_query_kernel<IMPL, true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
@@ -1162,7 +1144,8 @@ static int launch_query(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int
 // spread over the chunk's pairs -- a CTA that has to wait for a slot would leave its pair without workers while the
 // others run -- and never more than one warp per task (32 queries; 4 for small pairs).
 static int query_ctas_per_pair(const IcpWorkspace& w, int impl) {
-    int per_pair = (148 * (impl == 1 ? R3D_LEAN_MIN_CTAS : R3D_TILE_MIN_CTAS)) / w.n_pairs;
+    (void)impl;
+    int per_pair = (148 * R3D_LEAN_MIN_CTAS) / w.n_pairs;
     const int per_cta = queries_per_task(w.max_src) * (NN_THREADS / 32);
     const int cap = (w.max_src + per_cta - 1) / per_cta;
     if (per_pair > cap) per_pair = cap;
@@ -1173,8 +1156,7 @@ static int query_ctas_per_pair(const IcpWorkspace& w, int impl) {
 static int launch_nn(IcpWorkspace& w, bool seeded, bool fused, int write_d2, cudaStream_t st) {
     const int impl = g_nn_impl.load();
     const dim3 grid(query_ctas_per_pair(w, impl), w.n_pairs);
-    if (impl == 1) return launch_query<1>(w, grid, seeded, fused, write_d2, st);
-    return launch_query<2>(w, grid, seeded, fused, write_d2, st);
+    return launch_query<1>(w, grid, seeded, fused, write_d2, st);
 }
 
 static int sort_source(IcpWorkspace& w, const Point4* src, const int32_t* src_off, cudaStream_t st) {
@@ -1389,13 +1371,16 @@ extern "C" int r3d_set_option(int option, double value) {
     switch (option) {
         case R3D_OPT_NN_IMPL: {
             const int impl = (int)value;
-            if (impl != 1 && impl != 2) return R3D_ERR_INVALID;
+            if (impl != 1) return R3D_ERR_INVALID;
             g_nn_impl.store(impl);
             return R3D_OK;
         }
         case R3D_OPT_GROUP_SEARCH_MAX:
             if (!(value >= 0.0 && value <= 32.0)) return R3D_ERR_INVALID;
             g_group_max.store((int)value);
+            return R3D_OK;
+        case R3D_OPT_SLACK_CLAMP:
+            g_slack_clamp.store(value != 0.0 ? 1 : 0);
             return R3D_OK;
         case R3D_OPT_K4B_FP32:
             g_k4b_fp32.store(value != 0.0 ? 1 : 0);

@@ -1,8 +1,7 @@
 // Warp-union exact nearest-neighbour search on the sparse-block grid.
 //
 // Contract: exact NN, lowest-index tie-break, equal to float64 brute force (utils/icp.py:58-71 up to
-// exact ties).  This is round 1's search, kept as the cross-check of tile_search.cuh (the default since
-// round 2; select this one with R3D_OPT_NN_IMPL = 1).  A warp owns 32 consecutive queries of the
+// exact ties).  A warp owns 32 consecutive queries of the
 // spatially sorted source cloud, shares ONE candidate stream, and every lane evaluates every
 // candidate that survives a box filter:
 //   1. every lane turns its upper bound into a ball and the ball into a box of cells; the warp
@@ -215,9 +214,8 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
                 } else {
                     const int iy = loy + k1, iz = loz + k2;
                     const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
-                    const uint32_t* cs = v.cell_start + (size_t)b * 64 + (((iz & 3) << 4) | ((iy & 3) << 2));
-                    s = __ldg(cs + x0);
-                    cnt = __ldg(cs + x1 + 1) - s;
+                    const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
+                    cell_range(v, b, f + x0, f + x1 + 1, s, cnt);
                 }
             }
         }
@@ -604,9 +602,8 @@ __device__ __forceinline__ unsigned group_search(unsigned todo, const Best& seed
                 const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
                 if (b >= 0) {
                     const int x0 = max(lox, cbx * 4) - cbx * 4, x1 = min(hix, cbx * 4 + 3) - cbx * 4;
-                    const uint32_t* cs = v.cell_start + (size_t)b * 64 + (((iz & 3) << 4) | ((iy & 3) << 2));
-                    s = __ldg(cs + x0);
-                    cnt = __ldg(cs + x1 + 1) - s;
+                    const int f = ((iz & 3) << 4) | ((iy & 3) << 2);
+                    cell_range(v, b, f + x0, f + x1 + 1, s, cnt);
                 }
             }
             // the group's candidate stream = concatenation of its eight segments

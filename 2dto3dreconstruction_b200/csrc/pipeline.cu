@@ -5,6 +5,7 @@
 // tiny per-pair kernels (solve, scans) of one chunk overlap the wide kernels of another and, in the
 // host variant, the H2D copy of the next chunk overlaps compute.
 #include "grid.cuh"
+#include <mutex>
 #include <vector>
 
 namespace r3d {
@@ -53,8 +54,55 @@ __global__ void counts_kernel(const int32_t* __restrict__ src_off, const int32_t
     if (n_dst) n_dst[i] = dst_off[i + 1] - dst_off[i];
 }
 
+// ---- side streams --------------------------------------------------------------------------------------------
+constexpr int MAX_STREAMS = 4;
+struct StreamSet {
+    cudaStream_t streams[MAX_STREAMS];
+    cudaEvent_t done[MAX_STREAMS];
+    cudaEvent_t fork;
+    int device;
+    bool pooled;
+};
+std::mutex g_pool_mutex;
+std::vector<StreamSet*> g_pool_free;      // idle sets of any device (a handful at most)
+
+int make_stream_set(StreamSet*& out, int device) {
+    StreamSet* s = new StreamSet();
+    s->device = device;
+    s->pooled = true;
+    cudaError_t e = cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming);
+    for (int k = 0; k < MAX_STREAMS && e == cudaSuccess; k++) {
+        e = cudaStreamCreateWithFlags(&s->streams[k], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) { set_cuda_error(e, "stream pool"); delete s; return R3D_ERR_CUDA; }      // (process is in trouble anyway)
+    out = s;
+    return R3D_OK;
+}
+
+int acquire_streams(StreamSet*& out) {
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return R3D_ERR_CUDA;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (size_t k = 0; k < g_pool_free.size(); k++) {
+            if (g_pool_free[k]->device == device) {
+                out = g_pool_free[k];
+                g_pool_free.erase(g_pool_free.begin() + (long)k);
+                return R3D_OK;
+            }
+        }
+    }
+    return make_stream_set(out, device);
+}
+
+void release_streams(StreamSet* s) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pool_free.push_back(s);
+}
+
 int default_ppc(int ppc) { return ppc > 0 ? ppc : 16; }
-int default_streams(int s) { return s > 0 ? (s > 4 ? 4 : s) : 3; }
+int default_streams(int s) { return s > 0 ? (s > MAX_STREAMS ? MAX_STREAMS : s) : 3; }
 
 int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool host_input, int n_pairs, int h, int w, double fx,
                   double fy, double cx, double cy, const r3d_icp_params* params, int ppc, int n_streams, double* T_out,
@@ -85,19 +133,22 @@ int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool hos
     }
     if (!arena.ok) return R3D_ERR_WORKSPACE;
 
-    // streams + fork/join events (created per call: a call covers hundreds of launches)
-    std::vector<cudaStream_t> streams(n_streams);
-    std::vector<cudaEvent_t> done(n_streams);
-    cudaEvent_t fork;
-    R3D_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-    for (int s = 0; s < n_streams; s++) {
-        R3D_CUDA(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
-        R3D_CUDA(cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming));
+    // side streams + fork/join events: created once per process and device, lent to one call at a time (a concurrent call
+    // from another host thread gets a set of its own and destroys it afterwards)
+    StreamSet* set = nullptr;
+    int rc = acquire_streams(set);
+    if (rc != R3D_OK) return rc;
+    cudaStream_t* streams = set->streams;
+    cudaEvent_t* done = set->done;
+    cudaEvent_t fork = set->fork;
+    cudaError_t e0 = cudaEventRecord(fork, user_stream);
+    for (int s = 0; s < n_streams && e0 == cudaSuccess; s++) e0 = cudaStreamWaitEvent(streams[s], fork, 0);
+    if (e0 != cudaSuccess) {
+        set_cuda_error(e0, "register_depth_pairs fork");
+        release_streams(set);
+        return R3D_ERR_CUDA;
     }
-    R3D_CUDA(cudaEventRecord(fork, user_stream));
-    for (int s = 0; s < n_streams; s++) R3D_CUDA(cudaStreamWaitEvent(streams[s], fork, 0));
 
-    int rc = R3D_OK;
     int chunk_index = 0;
     for (int first = 0; first < n_pairs && rc == R3D_OK; first += ppc, chunk_index++) {
         const int np = (n_pairs - first < ppc) ? (n_pairs - first) : ppc;
@@ -108,9 +159,10 @@ int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool hos
         const uint16_t* d_dst = depth_dst + (size_t)first * hw;
         if (host_input) {
             // stage the chunk's frames; the copy of this chunk overlaps the kernels of the other streams
-            R3D_CUDA(cudaMemcpyAsync(c.depth, d_src, (size_t)np * hw * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
-            R3D_CUDA(cudaMemcpyAsync(c.depth + (size_t)np * hw, d_dst, (size_t)np * hw * sizeof(uint16_t),
-                                     cudaMemcpyHostToDevice, st));
+            cudaError_t ec = cudaMemcpyAsync(c.depth, d_src, (size_t)np * hw * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
+            if (ec == cudaSuccess)
+                ec = cudaMemcpyAsync(c.depth + (size_t)np * hw, d_dst, (size_t)np * hw * sizeof(uint16_t), cudaMemcpyHostToDevice, st);
+            if (ec != cudaSuccess) { set_cuda_error(ec, "register_depth_pairs H2D"); rc = R3D_ERR_CUDA; break; }
             d_src = c.depth;
             d_dst = c.depth + (size_t)np * hw;
         }
@@ -150,11 +202,7 @@ int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool hos
     }
     cudaError_t e = cudaSuccess;
     if (host_input) e = cudaStreamSynchronize(user_stream);
-    for (int s = 0; s < n_streams; s++) {
-        cudaStreamDestroy(streams[s]);   // deferred until the stream's work completes
-        cudaEventDestroy(done[s]);
-    }
-    cudaEventDestroy(fork);
+    release_streams(set);      // (work still queued on the side streams is ordered before anything a later call puts there)
     if (rc != R3D_OK) return rc;
     if (e != cudaSuccess) { set_cuda_error(e, "register_depth_pairs sync"); return R3D_ERR_CUDA; }
     e = cudaGetLastError();

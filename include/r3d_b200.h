@@ -265,9 +265,8 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* Tuning knobs; none of them changes results (process-wide, read when a call is issued).
- *   R3D_OPT_NN_IMPL        1 = warp-union walk (default, csrc/lean_search.cuh), 2 = tile search (csrc/tile_search.cuh: blocks staged
- *                          into shared memory by TMA, per-lane walk, fp32 filter + fp64 decision; exact too, slower on the bench
- *                          workload -- profiles/r02_nn_tile_search.md)
+ *   R3D_OPT_NN_IMPL        1 (the only value: the search of csrc/lean_search.cuh; round 2's TMA-staged tile search was exact and
+ *                          slower -- profiles/r02_nn_tile_search.md -- and has been removed; the option stays for ABI stability)
  *   R3D_OPT_FORCE_UNFUSED  non-zero: partial_set_size == 1 also runs through the selection + moments kernels (test knob)
  *   R3D_OPT_CELL_FACTOR    automatic grid cell edge in units of the estimated point spacing (used when cell_size <= 0; default 2)
  *   R3D_OPT_SLACK_MULT, R3D_OPT_SLACK_MAX_FRAC
@@ -277,11 +276,13 @@ int r3d_register_depth_pairs_host(const uint16_t* depth_src_host, const uint16_t
  *   R3D_OPT_GROUP_SEARCH_MAX  0..32 (default 12): seeded tasks of the ICP loop in which at most this many of the 32 lanes still
  *                          search are served by csrc/lean_search.cuh group_search (eight lanes per query, only that query's
  *                          own cells) instead of the warp-union walk; 0 = always the union walk
+ *   R3D_OPT_SLACK_CLAMP    non-zero: a query that moves too fast for the SLACK_MULT rule still widens its ball by SLACK_MAX_FRAC cells
+ *                          (instead of not at all), which buys it a skip budget for the next iteration or two
  *   R3D_OPT_K4B_FP32       non-zero: r3d_ransac3d_score filters in fp32 and redoes the residual in fp64 inside the rounding band
  *                          (same counts as the default all-fp64 kernel; measured slower, kept as the cross-check) */
 typedef enum {
     R3D_OPT_CELL_FACTOR = 2, R3D_OPT_NN_IMPL = 3, R3D_OPT_SLACK_MULT = 4, R3D_OPT_SLACK_MAX_FRAC = 5, R3D_OPT_FORCE_UNFUSED = 6,
-    R3D_OPT_GROUP_SEARCH_MAX = 7, R3D_OPT_K4B_FP32 = 8
+    R3D_OPT_GROUP_SEARCH_MAX = 7, R3D_OPT_K4B_FP32 = 8, R3D_OPT_SLACK_CLAMP = 9
 } r3d_option;
 int r3d_set_option(int option, double value);
 

@@ -46,6 +46,7 @@ for cfg in configs.split(","):
     impl, group, factor = parts[:3]
     mult, maxfrac = (parts[3], parts[4]) if len(parts) >= 5 else ("8", "0.25")
     cache = parts[5] if len(parts) >= 6 else "12"
+    assert L.r3d_set_option(9, float(parts[6]) if len(parts) >= 7 else 0.0) == 0
     assert L.r3d_set_option(7, float(cache)) == 0
     assert L.r3d_set_option(4, float(mult)) == 0
     assert L.r3d_set_option(5, float(maxfrac)) == 0
@@ -67,9 +68,9 @@ for cfg in configs.split(","):
         ref = T
     dev = float((T - ref).abs().max())
     nq = int(out["n_src"].sum())
-    print("impl %s G %2s factor %s slack %sx<=%s group<=%s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
+    print("clamp %s | impl %s G %2s factor %s slack %sx<=%s group<=%s: chunk %.3f ms  %.1f pairs/s | nn kernel %.3f ms over %d launches, avg %.1f us, "
           "%.2f G corr/s in kernel | max|T - T0| %.2e err0 %.6f" % (
-              impl, group, factor, mult, maxfrac, cache, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
+              parts[6] if len(parts) >= 7 else "0", impl, group, factor, mult, maxfrac, cache, dt * 1e3, pairs / dt, ms.value, n.value, 1e3 * ms.value / max(n.value, 1),
               nq * n.value / max(ms.value, 1e-9) / 1e6, dev, float(out["mean_err"][0])), flush=True)
     if stats_on:
         sx = (ctypes.c_uint64 * 32)()
