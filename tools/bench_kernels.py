@@ -72,10 +72,17 @@ def run(sections=None, icp_partials=(1.0, 0.7)):
         ms = timed(k1)
         nvalid = int(off[-1].item())
         algo = 2 * F * 480 * 640 + 32 * nvalid
-        out["K1_backproject"] = {"what": "%d frames 640x480 u16 -> xyzw fp64, pinhole (3 launches: count, scan, write)" % F, "ms": ms,
+        # K1 writes 15x what it reads, and HBM writes are slower than the read + write mix of a copy: the write-only rate of
+        # the device (a fill of as many bytes as K1 stores) is the roofline that applies
+        fill = torch.empty(32 * nvalid, dtype=torch.uint8, device=dev)
+        ms_fill = timed(lambda: fill.zero_())
+        out["K1_backproject"] = {"what": "%d frames 640x480 u16 -> xyzw fp64, pinhole (one pass: ticketed 4096-pixel tiles, chained scan with "
+                                         "decoupled look-back)" % F, "ms": ms,
                                  "frames_per_s": F / ms * 1e3, "algorithmic_bytes": algo, "achieved_gbs": algo / ms / 1e6,
-                                 "frac_of_hbm": algo / ms / 1e6 / HBM,
-                                 "note": "count re-reads the depth once more (2 B/pixel): traffic = algorithmic + 2*H*W per frame"}
+                                 "frac_of_hbm": algo / ms / 1e6 / HBM, "stored_gbs": 32 * nvalid / ms / 1e6,
+                                 "write_only_peak_gbs": 32 * nvalid / ms_fill / 1e6, "frac_of_write_only_peak": ms_fill / ms,
+                                 "note": "bound = HBM WRITE bandwidth: a fill (torch zero_) of the same number of bytes takes %.3f ms; "
+                                         "frac_of_hbm is against the measured copy peak (reads + writes)" % ms_fill}
 
     # ---- grid build + one unseeded query (r3d_nn_batch) on 8 pairs ----------------------------------------------
     if need_pairs:
