@@ -48,8 +48,10 @@ def _batched(depth_images, mode, scale):
 
 def depth_images_to_3d_pts(depth_images, scale=1.):
     """reconstruct.py:336-344."""
-    if isinstance(scale, (int, np.integer)) and int(scale) != 1:
-        raise NotImplementedError("integer scale other than 1 is not supported by the CUDA path; pass a float")
+    if isinstance(scale, (int, np.integer)) and not isinstance(scale, bool) and int(scale) != 1:
+        # integer arithmetic that wraps in int16 (utils/utils.py:40): the per-frame drop-in reproduces NumPy's rules
+        from .utils.utils import depth_to_voxel
+        return [depth_to_voxel(f, scale) for f in depth_images]
     out = _batched(depth_images, ops.BP_PIXEL, scale)
     if isinstance(scale, (int, np.integer)):
         out = [o.astype(np.int64) for o in out]

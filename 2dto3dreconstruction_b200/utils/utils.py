@@ -25,24 +25,35 @@ def _device_depth(img):
     elif a.dtype == np.uint8:
         a = a.astype(np.uint16)
     elif np.issubdtype(a.dtype, np.integer):
-        # astype(int16) keeps the low 16 bits of any integer type; uint16 holds the same bits,
-        # but x/y use the full value, so only in-range images can go through the u16 path
+        # astype(int16) keeps the low 16 bits of any integer type while x / y use the full value.  In-range images go through
+        # the u16 path (same bits); anything else that fits int32 through the float64 path, whose z is (int16)(int32)d -- the
+        # same low 16 bits -- and whose x / y are exact in double
         if a.size and (a.min() < 0 or a.max() > 65535):
-            raise NotImplementedError("integer depth outside [0, 65535] is not supported by the CUDA path")
-        a = a.astype(np.uint16)
+            if a.min() < -2**31 or a.max() > 2**31 - 1:
+                raise NotImplementedError("integer depth outside the int32 range is not supported by the CUDA path")
+            a = a.astype(np.float64)
+        else:
+            a = a.astype(np.uint16)
     else:
         a = a.astype(np.float64)
     return t.from_numpy(a[None]).cuda()
 
 
 def _run(img, scale, mode):
-    if isinstance(scale, (int, np.integer)) and not isinstance(scale, bool) and int(scale) != 1:
-        # int16 * python-int stays int16 in NumPy and can wrap; not reproduced on the device
-        raise NotImplementedError("integer scale other than 1 is not supported by the CUDA path; pass a float")
     d = _device_depth(img)
-    pts, off = ops.backproject(d, mode=mode, zscale=float(scale), layout=ops.LAYOUT_XYZ)
+    int_scale = isinstance(scale, (int, np.integer)) and not isinstance(scale, bool) and int(scale) != 1
+    pts, off = ops.backproject(d, mode=mode, zscale=1.0 if int_scale else float(scale), layout=ops.LAYOUT_XYZ)
     n = int(off[1].item())
-    return pts[:n].cpu().numpy()
+    out = pts[:n].cpu().numpy()
+    if int_scale:
+        # `img.astype(np.int16) * scale` with an INTEGER scale is integer arithmetic in NumPy: the product keeps the int16
+        # dtype and wraps (or NumPy refuses a scale that does not fit), and rows whose wrapped z is 0 are dropped
+        # (utils/utils.py:40-43).  The kernel delivered z = int16(depth); NumPy itself does the rest, so whatever the installed
+        # NumPy's promotion rules are, they are the reference's.
+        z = out[:, 2].astype(np.int16) * scale
+        out[:, 2] = z
+        out = out[z != 0]
+    return out
 
 
 def depth_to_voxel(img, scale=1):

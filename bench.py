@@ -32,10 +32,6 @@ ICP_ITERS = 30
 # 32 B source point + 32 B destination point (sorted cloud read once per launch, M ~ N)
 # + 4 B previous neighbour position read + 4 B new position written (SURVEY.md 8(d)'s 40 B is for float4 points)
 ALGO_BYTES_PER_CORR = 72.0
-# candidates evaluated per query by the warp-union walk (measured with the counter build,
-# profiles/r01_nn_sweeps.md) x 6 fp64 instructions each; FP64 pipe = 16 lanes/clk/SMSP, 592 SMSPs
-EVALS_PER_CORR = 80.0
-FP64_WARP_INSTR_PER_S = 592 * 1.965e9 / 2.0
 FALLBACK_HBM_GBS = 6650.0
 
 
@@ -46,7 +42,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("R3D_BENCH_PAIRS", "1024")), help="pairs per GPU")
-    ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "16")))
+    ap.add_argument("--pairs-per-chunk", type=int, default=int(os.environ.get("R3D_BENCH_PPC", "32")))
     ap.add_argument("--streams", type=int, default=int(os.environ.get("R3D_BENCH_STREAMS", "3")))
     ap.add_argument("--partial", type=float, default=1.0)
     ap.add_argument("--cpu-sample-iters", type=int, default=None,
@@ -361,42 +357,49 @@ def main():
     e2e_value = pairs_total / (e2e_ms / args.steps / 1000.0)
     peak, peak_src = peak_hbm()
     nn_avg_ms = nn_ms.value / max(nn_launches.value, 1)
-    # rank 0's nn launches processed rank 0's correspondences
-    achieved = ALGO_BYTES_PER_CORR * corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12) / 1e9
+    # rank 0's nn launches processed rank 0's correspondences.  The kernel is bound by instruction issue, not by HBM
+    # (DESIGN.md section 4): the primary fraction is warp instructions issued / issue slots, with the warp instructions per
+    # correspondence taken from the committed ncu capture of all 30 launches of a chunk (profiles/nn_kernel_traffic.json);
+    # the HBM figures (algorithmic bytes / measured copy peak) are kept beside it.
+    corr_in_kernel_per_s = corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12)
+    solo_corr_per_s = float(n_src[:solo_pairs].sum()) * ICP_ITERS / max(solo_ms.value / 1000.0, 1e-12)
+    hbm_achieved = ALGO_BYTES_PER_CORR * corr_in_kernel_per_s / 1e9
+    tf = {}
+    try:
+        tf = json.load(open(os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")))
+    except Exception:
+        pass
+    instr_per_corr = tf.get("warp_instructions_per_correspondence")
+    sm_hz = 1.0e6 * ((clocks or {}).get("sm_mhz") or 1965.0)
+    issue_peak = 592.0 * sm_hz      # one warp instruction per clock per SM sub-partition, 4 x 148 of them
     roofline = {
-        "bound": "hbm", "kernel": "nn_lean_kernel (K2 exact grid NN + fused K3 moments)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "bound": "issue" if instr_per_corr else "hbm",
+        "bound_note": "instruction issue slots of the 592 SM sub-partitions (non-tensor kernel: K = 3, fp64); the contract's "
+                      "hbm figures are hbm_achieved / hbm_peak / hbm_frac",
+        "kernel": "nn_query_kernel<1,1,1> (K2 exact grid NN: warp-union walk + group search, fused K3 moments)",
+        "achieved": (instr_per_corr * solo_corr_per_s / 1e9) if instr_per_corr else hbm_achieved,
+        "peak": issue_peak / 1e9 if instr_per_corr else peak,
+        "unit": "G warp-instructions/s" if instr_per_corr else "GB/s",
+        "traffic": None, "peak_source": "592 SMSPs x SM clock under load (%.0f MHz)" % (sm_hz / 1e6) if instr_per_corr else peak_src,
+        "warp_instructions_per_correspondence": instr_per_corr,
+        "hbm_achieved": hbm_achieved, "hbm_peak": peak, "hbm_frac": hbm_achieved / peak, "hbm_peak_source": peak_src,
+        "hbm_achieved_solo": ALGO_BYTES_PER_CORR * solo_corr_per_s / 1e9,
         "algorithmic_bytes_per_correspondence": ALGO_BYTES_PER_CORR, "launches_timed": int(nn_launches.value),
         "avg_launch_ms": nn_avg_ms, "kernel_share_of_step": nn_ms.value / (ms_total * args.streams),
         "share_note": "sum of the kernel's event-bracketed time / (timed region x %d streams): launches of different streams "
                       "overlap, so in-step durations include waiting for the other streams' kernels" % args.streams,
         "avg_launch_ms_solo": solo_ms.value / max(solo_launches.value, 1),
-        "achieved_solo": ALGO_BYTES_PER_CORR * float(n_src[:solo_pairs].sum()) * ICP_ITERS / max(solo_ms.value / 1000.0, 1e-12) / 1e9,
-        "correspondences_per_sec_in_kernel": corr_per_step * args.steps / max(nn_ms.value / 1000.0, 1e-12),
+        "correspondences_per_sec_in_kernel": corr_in_kernel_per_s,
+        "correspondences_per_sec_in_kernel_solo": solo_corr_per_s,
+        "note": "achieved = instructions per correspondence (ncu, whole chunk) x correspondences/s of the kernel timed alone "
+                "(one stream); in the step itself three streams share the issue slots",
     }
-    # what actually bounds the kernel: the FP64 pipe / issue slots of the candidate scan
-    solo_corr_per_s = float(n_src[:solo_pairs].sum()) * ICP_ITERS / max(solo_ms.value / 1000.0, 1e-12)
-    roofline["correspondences_per_sec_in_kernel_solo"] = solo_corr_per_s
-    fp64_instr_per_s = EVALS_PER_CORR * 6.0 / 32.0 * solo_corr_per_s
-    roofline["pipe"] = {"bound": "fp64 pipe (non-tensor)", "evaluations_per_correspondence": EVALS_PER_CORR,
-                        "achieved_fp64_warp_instr_per_s": fp64_instr_per_s, "peak_fp64_warp_instr_per_s": FP64_WARP_INSTR_PER_S,
-                        "frac": fp64_instr_per_s / FP64_WARP_INSTR_PER_S,
-                        "note": "kernel timed alone; nominal peak: 16 fp64 lanes/clk/SMSP x 592 SMSPs x 1965 MHz; evaluations "
-                                "per correspondence searched from the counter build (profiles/r01_nn_sweeps.md); skipped "
-                                "searches make the effective figure lower in late iterations"}
-    # DRAM traffic of the kernel from the committed ncu capture, scaled from the capture's launch size (8 pairs) to
-    # this run's (pairs_per_chunk pairs): bytes per correspondence x correspondences per launch
-    traffic_file = os.path.join(ROOT, "profiles", "nn_kernel_traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            tf = json.load(open(traffic_file))
-            per_corr = tf["dram_bytes_per_launch"] / float(tf["correspondences_per_launch"])
-            corr_per_launch = corr_per_step * args.steps / max(int(nn_launches.value), 1)
-            roofline["traffic"] = per_corr * corr_per_launch
-            roofline["traffic_bytes_per_correspondence"] = per_corr
-            roofline["traffic_source"] = tf.get("source")
-        except Exception:
-            pass
+    roofline["frac"] = roofline["achieved"] / roofline["peak"]
+    if "dram_bytes_per_correspondence" in tf:
+        corr_per_launch = corr_per_step * args.steps / max(int(nn_launches.value), 1)
+        roofline["traffic"] = tf["dram_bytes_per_correspondence"] * corr_per_launch
+        roofline["traffic_bytes_per_correspondence"] = tf["dram_bytes_per_correspondence"]
+        roofline["traffic_source"] = tf.get("source")
 
     cpu_baseline, parity = None, None
     if not args.no_cpu_baseline:

@@ -93,3 +93,29 @@ def test_fast_division_is_exact_over_the_whole_uint16_domain():
                 want = O.depth_to_voxel_ld(depth[k])
                 assert off[k + 1] - off[k] == want.shape[0]
                 assert np.array_equal(got[off[k]:off[k + 1]], want), (first + k)
+
+
+def test_integer_scale_and_wide_integer_depth_follow_numpy():
+    """depth_to_voxel / depth_to_voxel_ld with an INTEGER scale other than 1 (int16 arithmetic that wraps, rows whose wrapped z
+    is zero dropped) and with integer depth images outside the uint16 range (x / y from the full value, z from its low 16
+    bits): the drop-ins must return what the reference's NumPy expressions return (oracle = those expressions)."""
+    import warnings
+    utils = sub("utils.utils")
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 3000, size=(37, 53)).astype(np.uint16)
+    img[rng.random(img.shape) < 0.1] = 0
+    img[0, :4] = [256, 512, 16384, 32768]            # x 256 wraps to 0 in int16: those rows disappear
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for scale in (3, 256, -7):
+            for fn_name in ("depth_to_voxel", "depth_to_voxel_ld"):
+                want = getattr(O, fn_name)(img, scale)
+                got = getattr(utils, fn_name)(img, scale)
+                assert got.dtype == want.dtype and got.shape == want.shape, (fn_name, scale, got.shape, want.shape)
+                assert np.array_equal(got, want), (fn_name, scale)
+        wide = rng.integers(-70000, 200000, size=(29, 31)).astype(np.int32)
+        wide[::3, ::2] = 0
+        for fn_name in ("depth_to_voxel", "depth_to_voxel_ld"):
+            want = getattr(O, fn_name)(wide)
+            got = getattr(utils, fn_name)(wide)
+            assert got.shape == want.shape and np.array_equal(got, want.astype(got.dtype)), fn_name
