@@ -429,8 +429,17 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 // tasks with few searching lanes: eight lanes per query on that query's own cells (group_search); everything
                 // else, and whatever the groups could not take, through the warp-union walk
                 unsigned walk_m = __ballot_sync(0xffffffffu, active && !skip);
-                if (SEEDED && qpt == 32 && walk_m != 0u && __popc(walk_m) <= tune.group_max)
-                    walk_m = group_search(walk_m, seed, other, v, g, qx, qy, qz, slack, cover);
+                if (SEEDED && walk_m != 0u && tune.group_max > 0) {
+                    if (qpt == 32) {
+                        if (__popc(walk_m) <= tune.group_max) walk_m = group_search(walk_m, seed, other, v, g, qx, qy, qz, slack, cover);
+                    } else {
+                        // small pairs: the task's few queries sit on several lanes each (replicas); one group per query is
+                        // exactly the group search's shape.  The primary replicas own the results; a query the groups could
+                        // not take goes to the union walk with all its replicas.
+                        const unsigned un = group_search(walk_m & ((1u << qpt) - 1u), seed, other, v, g, qx, qy, qz, slack, cover);
+                        walk_m = __ballot_sync(0xffffffffu, active && !skip && ((un >> (lane & (qpt - 1))) & 1u));
+                    }
+                }
                 if (walk_m != 0u) {
                     float cover_w = 0.0f;
                     lean_search(ssm[warp].list, phase, seed, other, v, g, active && !skip && ((walk_m >> lane) & 1u), qx, qy, qz, slack, cover_w, qpt);
@@ -813,9 +822,10 @@ fsel_resolve_kernel(IcpWorkspace w) {
     __shared__ int s_cut;
     double* row = w.partial + ((size_t)pair * w.src_rows + (size_t)((n + 31) / 32)) * 16;
     const FSel fs = w.fsel[pair];
-    if (sel_is_small(n) || fs.all) {
+    if (sel_is_small(n)) return;      // (selected by sel_small_kernel; solve_kernel does not read a bracket row for them)
+    if (fs.all) {
         if (threadIdx.x < 16) row[threadIdx.x] = 0.0;
-        if (!sel_is_small(n) && threadIdx.x == 0) { st->tau = CUDART_INF; st->idx_cut = 0x7fffffff; }
+        if (threadIdx.x == 0) { st->tau = CUDART_INF; st->idx_cut = 0x7fffffff; }
         return;
     }
     const int c = (int)w.cand_n[pair];
@@ -959,7 +969,7 @@ solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
     __shared__ double m[16];
     const int n = st->n_src;
     // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32 + 1;      // (+ 1: the bracket row of fsel_resolve_kernel)
+    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32 + (sel_is_small(n) ? 0 : 1);      // (+ 1: the bracket row of fsel_resolve_kernel, large pairs)
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -1222,7 +1232,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
                     R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
             }
             R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
-            R3D_LAUNCH(fsel_resolve_kernel, P, SOLVE_THREADS, 0, st, w);
+            if (w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(fsel_resolve_kernel, P, SOLVE_THREADS, 0, st, w);
         }
         R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
     }
