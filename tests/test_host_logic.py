@@ -176,3 +176,25 @@ def test_bench_workload_generator_equals_the_oracle_generator():
         assert a.dtype == np.uint16 and np.array_equal(a, a2) and np.array_equal(b, b2)
     fa, fb = synth.depth_pairs(5, 2, 48, 64)
     assert np.array_equal(fa[1], O.synth_depth_pair(6, h=48, w=64)[0])
+
+
+def test_bench_helpers():
+    """bench.py's host-side pieces: both arms print the same `config` object, the parity numbers are north_star's two
+    quantities, and the reference arm and the CUDA arm agree on how many pairs they share."""
+    import argparse
+    import bench
+    args = argparse.Namespace(pairs=1024, partial=1.0, pairs_per_chunk=32, streams=3, scaling="weak")
+    c1, c2 = bench.make_config(args, 1), bench.make_config(args, 1)
+    assert c1 == c2 and c1["pairs_per_gpu"] == 1024 and c1["global_pairs"] == 1024 and "configs[2]" in c1["workload"]
+    c8 = bench.make_config(args, 8)
+    assert c8["pairs_per_gpu"] == 1024 and c8["global_pairs"] == 8192
+    args.scaling = "strong"
+    cs = bench.make_config(args, 8)
+    assert cs["pairs_per_gpu"] == 128 and cs["global_pairs"] == 1024
+    T = np.eye(4)
+    T2 = np.eye(4)
+    T2[:3, 3] = [3.0, 0.0, 4.0]
+    T2[0, 0] = 1.0 + 1e-5
+    dR, dt = bench.transform_gap(T2, T, 1000.0)
+    assert abs(dR - 1e-5) < 1e-12 and abs(dt - 5.0e-3) < 1e-12
+    assert 1 <= bench.n_shared_pairs(1024) <= 64 and bench.n_shared_pairs(3) <= 3

@@ -42,3 +42,5 @@ if has_stats:
         st[1] / tasks, st[2] / tasks, st[3] / tasks, st[4] / tasks, st[5] / tasks, st[6] / tasks))
     print("far searches/task %.3f, sweep steps/far %.1f, scan steps/far %.1f, block-granular walks/task %.3f | task cycles: mean %.0f, max %d" % (
         st[8] / tasks, st[9] / max(int(st[8]), 1), st[10] / max(int(st[8]), 1), st[11] / tasks, st[12] / tasks, st[13]))
+    print("group search: tasks %.3f of all, passes/task %.2f, candidate steps/task %.2f, queries sent on to the union walk per task %.2f" % (
+        st[16] / tasks, st[17] / tasks, st[19] / tasks, st[18] / tasks))
