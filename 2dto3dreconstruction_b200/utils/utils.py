@@ -15,8 +15,6 @@ from .. import ops
 
 def _device_depth(img):
     """One frame as a CUDA [1,H,W] tensor in a dtype the kernel reads natively."""
-    C.require_device()
-    t = C.torch()
     a = np.asarray(img)
     if a.ndim != 2:
         a = a.reshape(a.shape[0], a.shape[1])
@@ -36,7 +34,8 @@ def _device_depth(img):
             a = a.astype(np.uint16)
     else:
         a = a.astype(np.float64)
-    return t.from_numpy(a[None]).cuda()
+    C.require_device()
+    return C.torch().from_numpy(a[None]).cuda()
 
 
 def _run(img, scale, mode):

@@ -112,8 +112,8 @@ def test_drop_in_argument_errors_do_not_need_a_gpu():
     q9 = sub("utils.homography_utils.q9")
     with pytest.raises(IndexError):
         q9.make_binned_array((10, 10), np.array([[50.0, 2.0]]))
-    with pytest.raises(NotImplementedError):
-        sub("utils.utils").depth_to_voxel(np.zeros((4, 4), np.uint16), scale=2)
+    with pytest.raises(NotImplementedError):      # integer depth beyond int32: neither the u16 nor the float64 path reproduces astype(int16)
+        sub("utils.utils").depth_to_voxel(np.full((4, 4), 2**40, np.int64))
 
 
 def test_q9_host_side_dlt_matches_oracle():
