@@ -32,7 +32,7 @@ if os.environ.get("SLACK"):      # "mult,maxfrac"
     mult, frac = (float(x) for x in os.environ["SLACK"].split(","))
     L.r3d_set_option(4, mult), L.r3d_set_option(5, frac)
 L.r3d_set_option(7, float(os.environ.get("GROUP", "12")))
-per_lane = 32.0 if impl == 2 else 1.0      # the tile search counts evaluations summed over the lanes
+per_lane = 1.0
 print("iter  launch_us  rounds/task  searching lanes/task  candidates/lane  | per task: group-searched  passes  steps  sent on to the walk (lanes) | mean_err")
 for k in range(1, iters + 1):
     kw = dict(max_iterations=k, tolerance=0.0, partial_set_size=partial, pairs_per_chunk=pairs, n_streams=1)

@@ -77,12 +77,11 @@ for cfg in configs.split(","):
         L.r3d_nn_stats_read_ext(sx, 1)
         st = list(sx)[:8]
         tasks = max(int(st[0]), 1)
-        ev = st[2] / tasks / (32.0 if impl == "2" else 1.0)      # the tile search counts evaluations per lane, summed over the warp
+        ev = st[2] / tasks
         print("    per task of 32 queries: rounds %.2f, candidates/lane %.1f, lanes skipped %.2f, lookup rounds / staging passes %.2f, "
               "segments / block slots %.1f, non-empty / staged %.1f | violated skip bounds: %d" % (
                   st[1] / tasks, ev, st[3] / tasks, st[4] / tasks, st[5] / tasks, st[6] / tasks, st[7]), flush=True)
-        if impl == "2":
-            print("    tile search: fp64 re-evaluations per query %.2f, records staged per task %.1f" % (
-                sx[14] / tasks / 32.0, sx[15] / tasks), flush=True)
+        print("    group search: %.3f of the tasks, %.2f passes and %.2f candidate steps per task, %.2f queries per task sent on to the union walk" % (
+            sx[16] / tasks, sx[17] / tasks, sx[19] / tasks, sx[18] / tasks), flush=True)
         assert st[7] == 0, "a skipped lane saw a point closer than its seed"
     assert dev < 1e-9, "variants disagree"
