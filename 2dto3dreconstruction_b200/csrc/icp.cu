@@ -321,7 +321,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <int IMPL> struct SearchSmem;
 template <> struct SearchSmem<1> { double2 list[LEAN_WARP_SMEM]; };      // survivors list; never shared with the reduction: its stale slots must stay real points
 
-template <int IMPL, bool SEEDED, bool FUSED>
+// SMALL: every pair of the launch has at most NN_SMALL_PAIR source points (decided by the host from max_src): the search is
+// compiled with the block pruning of lean_search.cuh (PRUNE).
+template <int IMPL, bool SEEDED, bool FUSED, bool SMALL>
 __global__ void __launch_bounds__(NN_THREADS, R3D_LEAN_MIN_CTAS)
 nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
@@ -442,7 +444,9 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                 }
                 if (walk_m != 0u) {
                     float cover_w = 0.0f;
-                    lean_search(ssm[warp].list, phase, seed, other, v, g, active && !skip && ((walk_m >> lane) & 1u), qx, qy, qz, slack, cover_w, qpt);
+                    // (the walk's per-lane query table shares the warp's reduction scratch: the two are never live at the same time)
+                    lean_search<SMALL>(ssm[warp].list, reinterpret_cast<float4*>(scratch[warp]), phase, seed, other, v, g,
+                                active && !skip && ((walk_m >> lane) & 1u), qx, qy, qz, slack, cover_w, qpt);
                     if ((walk_m >> lane) & 1u) cover = cover_w;
                 }
                 lb_other = sqrtf(__double2float_rd(other.d2));
@@ -1140,13 +1144,16 @@ static int launch_query(IcpWorkspace& w, dim3 grid, bool seeded, bool fused, int
     tune.slack_max_frac = g_slack_max_frac.load();
     tune.group_max = g_group_max.load();
     tune.slack_clamp = g_slack_clamp.load();
+    const bool small = w.max_src <= NN_SMALL_PAIR;
+#define NN_LAUNCH(S, F, M) R3D_LAUNCH((nn_query_kernel<IMPL, S, F, M>), grid, NN_THREADS, 0, st, w, write_d2, tune)
     if (seeded) {
-        if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, true, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
-        else R3D_LAUNCH((nn_query_kernel<IMPL, true, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        if (fused) { if (small) NN_LAUNCH(true, true, true); else NN_LAUNCH(true, true, false); }
+        else { if (small) NN_LAUNCH(true, false, true); else NN_LAUNCH(true, false, false); }
     } else {
-        if (fused) R3D_LAUNCH((nn_query_kernel<IMPL, false, true>), grid, NN_THREADS, 0, st, w, write_d2, tune);
-        else R3D_LAUNCH((nn_query_kernel<IMPL, false, false>), grid, NN_THREADS, 0, st, w, write_d2, tune);
+        if (fused) { if (small) NN_LAUNCH(false, true, true); else NN_LAUNCH(false, true, false); }
+        else { if (small) NN_LAUNCH(false, false, true); else NN_LAUNCH(false, false, false); }
     }
+#undef NN_LAUNCH
     return R3D_OK;
 }
 

@@ -111,6 +111,8 @@ struct WarpList {
     int n;             // warp-uniform
     int nrep, rep;     // small pairs: every query sits on nrep = 4 (or 2) lanes, replica rep = lane / (32 / nrep); else nrep = 1, rep = 0
     double lo[3], hi[3];      // filter box (world coordinates)
+    float4* sq;               // [32] shared: every lane's query in cell coordinates (xyz) and the radius it asked for in cells
+                              // (w, margins included; < 0: the lane is not served by this round) -- for the block-granular walk
 #if R3D_LEAN_TMA
     const double2* stage;     // two staging buffers of 32 raw 32-byte records each, filled by cp.async.bulk
     uint32_t stage_addr;      // shared-window address of `stage`
@@ -170,7 +172,31 @@ __device__ __forceinline__ void list_init(double2* list, const Point4* __restric
     __syncwarp();
 }
 
+// A block-granular box is mostly corners no ball reaches (the box of a ball of 7 cells has 2.6x its volume, and the cloud is a
+// surface): a block is kept only if its cube comes within the radius of one of the served queries.  sq[j] = query j in cell
+// coordinates + the radius it asked for in cells (margins of the box computation included; < 0: not served by this round);
+// with replicated queries (small pairs) the n_q distinct ones sit on lanes 0 .. n_q - 1.  Float arithmetic: the test only has
+// to be conservative.  Out of line: block-granular walks are the exception, and inlined the loop costs the common row walk
+// registers.
+__device__ __noinline__ bool block_reached(const float4* sq, int n_q, int cbx, int cby, int cbz) {
+    const float cx0 = (float)(4 * cbx), cy0 = (float)(4 * cby), cz0 = (float)(4 * cbz);
+    bool reached = false;
+#pragma unroll 4
+    for (int j = 0; j < n_q; j++) {
+        const float4 a = sq[j];      // (broadcast)
+        const float dx = fmaxf(fmaxf(cx0 - a.x, a.x - (cx0 + 4.0f)), 0.0f), dy = fmaxf(fmaxf(cy0 - a.y, a.y - (cy0 + 4.0f)), 0.0f),
+                    dz = fmaxf(fmaxf(cz0 - a.z, a.z - (cz0 + 4.0f)), 0.0f);
+        reached = reached || (a.w >= 0.0f && fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= a.w * a.w);
+    }
+    return reached;
+}
+
 // Walk every cell of the warp's box [lo, hi] (warp-uniform ints; size limits: see lean_search).
+// PRUNE: block-granular walks keep only the blocks some served query's ball reaches (block_reached).  Compiled in for the
+// launches whose pairs are all small (the reference's sub-sampled, often badly aligned clouds, where such walks are the
+// rule: 15.2 -> 10.0 ms for the sofa pair's 100 iterations); in the kernel that serves the large pairs the extra live
+// state costs the common row walk 2 % (250 -> 256 us per launch on the bench workload) and the walks are rare.
+template <bool PRUNE>
 __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_pos, const GridView& v, const GridParams& g, int lox,
                                               int loy, int loz, int hix, int hiy, int hiz, double qx, double qy, double qz) {
     const int lane = threadIdx.x & 31;
@@ -206,7 +232,12 @@ __device__ __forceinline__ void lean_scan_box(WarpList& L, Best& best, int seed_
             const int cbx = bx0 + k0;
             const int cby = by_block ? by0 + k1 : (loy + k1) >> 2, cbz = by_block ? bz0 + k2 : (loz + k2) >> 2;
             const uint32_t key = (uint32_t)((cbz * g.by + cby) * g.bx + cbx);
-            const int b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
+            // (block-granular walk: only blocks that some served query's ball reaches; shared-memory reads only, so the
+            // call may sit in divergent code)
+            int b = -1;
+            bool wanted = true;
+            if constexpr (PRUNE) wanted = !by_block || block_reached(L.sq, 32 / L.nrep, cbx, cby, cbz);      // (shared-memory reads only: fine in divergent code)
+            if (wanted) b = find_block(v.hash, g.hash_mask, key, block_hash(cbx, cby, cbz));
             if (b >= 0) {
                 if (by_block) {
                     s = __ldg(v.block_first + b);
@@ -416,7 +447,9 @@ __device__ __forceinline__ float wmax_f(float v) { return sord2f(__reduce_max_sy
 __device__ __forceinline__ int cell_lo(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 
-__device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, const Best& seed, Best& other, const GridView& v,
+// `sq`: 32 float4 of shared memory owned by the warp (may be reused by the caller between calls; used with PRUNE only).
+template <bool PRUNE>
+__device__ __forceinline__ void lean_search(double2* list, float4* sq, unsigned& tma_phase, const Best& seed, Best& other, const GridView& v,
                                             const GridParams& g, bool active, double qx, double qy, double qz, float slack,
                                             float& cover, int qpt = 32) {
     // Cell coordinates in float.  The box only has to CONTAIN the ball, so every rounding is covered by a
@@ -440,6 +473,7 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
     // they evaluate, and are merged after every walk
     L.nrep = 32 / qpt;
     L.rep = (int)(threadIdx.x & 31) / qpt;
+    L.sq = sq;
 #if R3D_LEAN_TMA
     L.stage = list + 2 * LEAN_LIST_CAP;
     L.stage_addr = smem_u32(L.stage);
@@ -498,7 +532,12 @@ __device__ __forceinline__ void lean_search(double2* list, unsigned& tma_phase, 
             L.lo[0] = whole ? -CUDART_INF : (double)l0; L.hi[0] = whole ? CUDART_INF : (double)h0;
             L.lo[1] = whole ? -CUDART_INF : (double)l1; L.hi[1] = whole ? CUDART_INF : (double)h1;
             L.lo[2] = whole ? -CUDART_INF : (double)l2; L.hi[2] = whole ? CUDART_INF : (double)h2;
-            lean_scan_box(L, other, seed.pos, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
+            if constexpr (PRUNE) {
+                __syncwarp();
+                L.sq[threadIdx.x & 31] = make_float4(tqx, tqy, tqz, (part && !whole) ? rc + (mgx + mgy + mgz) : (part ? 3.0e18f : -1.0f));
+                __syncwarp();
+            }
+            lean_scan_box<PRUNE>(L, other, seed.pos, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
             if (part) {
                 const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                 fin = whole || (rn <= ruse) || !(ruse < 1e37f);
