@@ -414,10 +414,10 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                     const double mz = D[8] * a.x + D[9] * a.y + D[10] * a.z + D[11];
                     // rounded up; the last term covers the fp64 rounding of the two transformed positions themselves
                     // (a few ulps of the coordinates), which matters only when coordinates are ~1e9 times the distances
-                    const float moved = sqrtf(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
+                    const float moved = sqrt_bound(__double2float_ru(mx * mx + my * my + mz * mz)) * 1.000001f +
                                         __double2float_ru(4.0e-15 * (fabs(qx) + fabs(qy) + fabs(qz))) + 1e-30f;
                     left = __fsub_rd(budget[i], moved);
-                    skip = left > sqrtf(__double2float_ru(seed.d2)) * 1.000001f;
+                    skip = left > sqrt_bound(__double2float_ru(seed.d2)) * 1.000001f;
                     const float want = moved * tune.slack_mult;
                     slack = (want <= slack_max) ? want + 1e-4f * slack_max : (tune.slack_clamp ? slack_max : 0.0f);
                 }
@@ -449,7 +449,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
                                 active && !skip && ((walk_m >> lane) & 1u), qx, qy, qz, slack, cover_w, qpt);
                     if ((walk_m >> lane) & 1u) cover = cover_w;
                 }
-                lb_other = sqrtf(__double2float_rd(other.d2));
+                lb_other = sqrt_bound(__double2float_rd(other.d2));
             }
             const bool seed_wins = skip || !(other.d2 < seed.d2 || (other.d2 == seed.d2 && other.idx < seed.idx));
 #ifdef R3D_NN_STATS

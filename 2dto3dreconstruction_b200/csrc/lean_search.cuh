@@ -441,8 +441,26 @@ __device__ __forceinline__ int f2sord(float f) {
     return b ^ ((b >> 31) & 0x7fffffff);
 }
 __device__ __forceinline__ float sord2f(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
-__device__ __forceinline__ float wmin_f(float v) { return sord2f(__reduce_min_sync(0xffffffffu, f2sord(v))); }
-__device__ __forceinline__ float wmax_f(float v) { return sord2f(__reduce_max_sync(0xffffffffu, f2sord(v))); }
+// warp minimum / maximum of floats: sm_100a reduces fp32 in one instruction (CREDUX.MIN/MAX.F32; NaN inputs are ignored, as by
+// fminf / fmaxf) -- the order-preserving integer map above is what older parts needed
+__device__ __forceinline__ float wmin_f(float v) {
+    float r;
+    asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+__device__ __forceinline__ float wmax_f(float v) {
+    float r;
+    asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+    return r;
+}
+// Square root for BOUNDS: sqrt.approx.f32 (MUFU.SQRT, denormals handled) is within 2^-23 relative of the exact root, half of
+// what the IEEE sequence costs; every use multiplies by 1 +- 1e-6 (= 2^-19.9) towards the safe side, which covers it together
+// with the roundings of the conversion before and the product after.
+__device__ __forceinline__ float sqrt_bound(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 // cell index of a float cell coordinate, clamped into [0, n-1] (NaN -> 0)
 __device__ __forceinline__ int cell_lo(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
 __device__ __forceinline__ int cell_hi(float t, int n) { return min(max(__float2int_rd(t), 0), n - 1); }
@@ -497,7 +515,7 @@ __device__ __forceinline__ void lean_search(double2* list, float4* sq, unsigned&
         R3D_STAT(1, 1);
         const int leader = __ffs(unfin) - 1;
         // float sqrt rounded up
-        const float rl = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
+        const float rl = sqrt_bound((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
         const float ruse = fminf(rl + slack, rcap);
         const float rc = ruse * inv_cell;
         const int mlox = cell_lo(tqx - rc - mgx, g.nx), mhix = cell_hi(tqx + rc + mgx, g.nx);
@@ -514,14 +532,17 @@ __device__ __forceinline__ void lean_search(double2* list, float4* sq, unsigned&
         const int loy = __reduce_min_sync(FULL, part ? mloy : big), hiy = __reduce_max_sync(FULL, part ? mhiy : -1);
         const int loz = __reduce_min_sync(FULL, part ? mloz : big), hiz = __reduce_max_sync(FULL, part ? mhiz : -1);
         const bool whole = lox == 0 && loy == 0 && loz == 0 && hix == g.nx - 1 && hiy == g.ny - 1 && hiz == g.nz - 1;
-        const long long nseg = (long long)(hiy - loy + 1) * (hiz - loz + 1) * ((hix >> 2) - (lox >> 2) + 1);
-        const long long nblk = (long long)((hiy >> 2) - (loy >> 2) + 1) * ((hiz >> 2) - (loz >> 2) + 1) * ((hix >> 2) - (lox >> 2) + 1);
+        // (counts as float products: exact below 2^24, and anything larger is above both limits below -- an axis has up to
+        // 2^20 cells, so the integer products would need 64 bits)
+        const float nxbf = (float)((hix >> 2) - (lox >> 2) + 1);
+        const float nseg = (float)(hiy - loy + 1) * (float)(hiz - loz + 1) * nxbf;
+        const float nblk = (float)((hiy >> 2) - (loy >> 2) + 1) * (float)((hiz >> 2) - (loz >> 2) + 1) * nxbf;
         // small boxes are walked row by row, larger ones block by block.  A box of more than LEAN_BLOCKS_MAX block slots
         // that is also a large part of the cloud (more than an eighth of its occupied blocks: a small cloud with far
         // outliers, a badly misaligned pair) is searched one query at a time by sweeping the cloud's block list with
         // distance pruning; in a large cloud the same number of slots is a small neighbourhood and is still walked
         // (the sweep costs n_blocks / 32 steps per query, the walk nblk / 32 lookups per warp).
-        if (nseg <= (long long)LEAN_ROW_SEGS_MAX || nblk <= max((long long)LEAN_BLOCKS_MAX, (long long)(g.n_blocks >> 3))) {
+        if (nseg <= (float)LEAN_ROW_SEGS_MAX || nblk <= (float)max(LEAN_BLOCKS_MAX, g.n_blocks >> 3)) {
             // the union of the served balls' bounding boxes in world coordinates: a point outside it is
             // outside every served ball.  When the box is the whole grid everything is looked at once and
             // the answer is final for every lane, so nothing may be filtered.
@@ -539,7 +560,7 @@ __device__ __forceinline__ void lean_search(double2* list, float4* sq, unsigned&
             }
             lean_scan_box<PRUNE>(L, other, seed.pos, v, g, lox, loy, loz, hix, hiy, hiz, qx, qy, qz);
             if (part) {
-                const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
+                const float rn = sqrt_bound((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                 fin = whole || (rn <= ruse) || !(ruse < 1e37f);
                 if (fin) cover = whole ? inf : ruse;
                 rcap *= 2.0f;   // a poor bound (a point seen in a far corner of the union) must not set the next radius
@@ -555,7 +576,7 @@ __device__ __forceinline__ void lean_search(double2* list, float4* sq, unsigned&
                 const Best found = far_query_search(owner, seed, v, g, qx, qy, qz, ruse, all_scanned);
                 if ((int)(threadIdx.x & 31) % qpt == owner) {
                     if (found.d2 < other.d2 || (found.d2 == other.d2 && found.idx < other.idx)) other = found;
-                    const float rn = sqrtf((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
+                    const float rn = sqrt_bound((float)fmin(seed.d2, other.d2)) * 1.000001f + 1e-30f;
                     fin = all_scanned || (rn <= ruse) || !(ruse < 1e37f);
                     if (fin) cover = all_scanned ? inf : ruse;
                     rcap *= 2.0f;
@@ -588,7 +609,7 @@ __device__ __forceinline__ unsigned group_search(unsigned todo, const Best& seed
                 tqz = (float)((qz - g.oz) * g.inv_cell);
     const float mgx = fmaf(fabsf(tqx), 2.4e-7f, 2e-3f), mgy = fmaf(fabsf(tqy), 2.4e-7f, 2e-3f),
                 mgz = fmaf(fabsf(tqz), 2.4e-7f, 2e-3f);
-    const float rl = sqrtf((float)seed.d2) * 1.000001f + 1e-30f;
+    const float rl = sqrt_bound((float)seed.d2) * 1.000001f + 1e-30f;
     const float ruse = rl + slack;
     const float rc = ruse * ((float)g.inv_cell * 1.000001f);
     const int mlox = cell_lo(tqx - rc - mgx, g.nx), mhix = cell_hi(tqx + rc + mgx, g.nx);
