@@ -15,6 +15,7 @@
 //                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126)
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
+#include <type_traits>
 #include "lean_search.cuh"
 #include <mutex>
 #include <vector>
@@ -353,7 +354,12 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     int32_t* nn_pos = w.nn_pos + (size_t)pair * w.max_src;
     float* budget = w.budget + (size_t)pair * w.max_src;
     double* d2_out = w.d2 + (size_t)pair * w.max_src;
-    const int qpt = queries_per_task(s_n);
+    // The task size is a compile-time constant in the launches whose pairs are all small (QPT = R3D_NN_SMALL_QPT: 1-4 % off
+    // their nn launches) and read from the pair's size otherwise (QPT = 0).  A second, QPT = 32 copy of the loop for the large
+    // pairs was measured: 1.7 % fewer warp instructions (the replica paths fold away), no change in time, twice the code.
+    auto run = [&](auto qpt_c) {
+    constexpr int QPT = decltype(qpt_c)::value;
+    const int qpt = QPT > 0 ? QPT : queries_per_task(s_n);
     const int n_tasks = (s_n + qpt - 1) / qpt;
     const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
@@ -489,6 +495,12 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             }
         }
         if (FUSED && lane < 16) w.partial[((size_t)pair * w.src_rows + (size_t)vw) * 16 + lane] = acc;
+    }
+    };      // run
+    if constexpr (SMALL) {
+        run(std::integral_constant<int, (NN_MID_PAIR > 0 ? 0 : R3D_NN_SMALL_QPT)>{});
+    } else {
+        run(std::integral_constant<int, 0>{});
     }
 }
 
@@ -746,9 +758,17 @@ __device__ __forceinline__ bool kept(double d2, int i, double tau, int idx_cut) 
     return d2 < tau || (d2 == tau && i <= idx_cut);
 }
 
-// Moments over the kept correspondences, one row per 32 queries.  Small pairs: tau / idx_cut are final (sel_small_kernel).
-// Large pairs: everything below the bracket of the k-th smallest distance is kept and summed here; the bracket's members are
-// listed for fsel_resolve_kernel; everything above is dropped.
+// Moments over the kept correspondences.  A CTA takes MOM_TILE = NN_THREADS x MOM_PT consecutive queries, MOM_PT per thread
+// (query base + r NN_THREADS + thread: coalesced), each thread summing its own in order before ONE warp reduction: a row of the
+// pair's table per warp and tile, i.e. per 32 x MOM_PT queries (mom_rows() of them), a fixed order whatever the launch.  (One
+// query per thread and a row per 32 queries made the reductions -- not the 76 bytes per correspondence -- the kernel's cost, and
+// gave solve_kernel four times the rows to add.)  Small pairs: tau / idx_cut are final (sel_small_kernel).  Large pairs:
+// everything below the bracket of the k-th smallest distance is kept and summed here; the bracket's members are listed for
+// fsel_resolve_kernel; everything above is dropped.
+constexpr int MOM_PT = 4;
+constexpr int MOM_TILE = NN_THREADS * MOM_PT;
+__host__ __device__ __forceinline__ int mom_rows(int n_src) { return ((n_src + MOM_TILE - 1) / MOM_TILE) * (NN_THREADS / 32); }
+
 __global__ void __launch_bounds__(NN_THREADS)
 moments_kernel(IcpWorkspace w) {
     const int pair = blockIdx.y;
@@ -761,59 +781,63 @@ moments_kernel(IcpWorkspace w) {
     __syncthreads();
     if (threadIdx.x < 12) T[threadIdx.x] = s.T[threadIdx.x];
     __syncthreads();
-    if (s.done || blockIdx.x * NN_THREADS >= s.n_src) return;
-    const int i = blockIdx.x * NN_THREADS + threadIdx.x;
+    if (s.done || blockIdx.x * MOM_TILE >= s.n_src) return;
     const bool small = sel_is_small(s.n_src);
+    const int lane = threadIdx.x & 31;
     double m[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) m[k] = 0.0;
-    bool member = false;
-    if (i < s.n_src) {
-        // the three streams indexed by i are requested together (one memory latency instead of two before the gather)
-        const double d2 = w.d2[(size_t)pair * w.max_src + i];
-        const int pos = w.nn_pos[(size_t)pair * w.max_src + i];
-        const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
-        bool keep;
-        if (small) {
-            keep = kept(d2, i, s.tau, s.idx_cut);
-        } else {
-            const uint32_t k22 = key32(d2) >> 10;
-            keep = fs.all || k22 < fs.prefix;
-            member = !fs.all && k22 == fs.prefix;
+#pragma unroll 1
+    for (int r = 0; r < MOM_PT; r++) {
+        const int i = blockIdx.x * MOM_TILE + r * NN_THREADS + threadIdx.x;
+        bool member = false;
+        if (i < s.n_src) {
+            // the three streams indexed by i are requested together (one memory latency instead of two before the gather)
+            const double d2 = w.d2[(size_t)pair * w.max_src + i];
+            const int pos = w.nn_pos[(size_t)pair * w.max_src + i];
+            const Point4 a = load_point(w.src_sorted + (size_t)pair * w.max_src + i);
+            bool keep;
+            if (small) {
+                keep = kept(d2, i, s.tau, s.idx_cut);
+            } else {
+                const uint32_t k22 = key32(d2) >> 10;
+                keep = fs.all || k22 < fs.prefix;
+                member = !fs.all && k22 == fs.prefix;
+            }
+            if (keep) {
+                const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
+                const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
+                const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
+                const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + pos);
+                double t[16];
+                accumulate_pair(t, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
+                                b.z - g.shift[2], sqrt(d2));
+#pragma unroll
+                for (int k = 0; k < 16; k++) m[k] += t[k];
+            }
         }
-        if (keep) {
-            const double qx = T[0] * a.x + T[1] * a.y + T[2] * a.z + T[3];
-            const double qy = T[4] * a.x + T[5] * a.y + T[6] * a.z + T[7];
-            const double qz = T[8] * a.x + T[9] * a.y + T[10] * a.z + T[11];
-            const Point4 b = load_point(w.grid.sorted + (size_t)pair * w.grid.max_dst + pos);
-            accumulate_pair(m, qx - g.shift[0], qy - g.shift[1], qz - g.shift[2], b.x - g.shift[0], b.y - g.shift[1],
-                            b.z - g.shift[2], sqrt(d2));
+        // members of the bracket: one slot each in the pair's list (warp-aggregated)
+        const unsigned mm = __ballot_sync(0xffffffffu, member);
+        if (mm) {
+            uint32_t base = 0;
+            if (lane == __ffs(mm) - 1) base = atomicAdd(w.cand_n + pair, (uint32_t)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mm) - 1);
+            if (member) w.cand_idx[(size_t)pair * w.max_src + base + __popc(mm & ((1u << lane) - 1u))] = i;
         }
-    }
-    // members of the bracket: one slot each in the pair's list (warp-aggregated)
-    const unsigned mm = __ballot_sync(0xffffffffu, member);
-    if (mm) {
-        const int lane = threadIdx.x & 31;
-        uint32_t base = 0;
-        if (lane == __ffs(mm) - 1) base = atomicAdd(w.cand_n + pair, (uint32_t)__popc(mm));
-        base = __shfl_sync(0xffffffffu, base, __ffs(mm) - 1);
-        if (member) w.cand_idx[(size_t)pair * w.max_src + base + __popc(mm & ((1u << lane) - 1u))] = i;
     }
     warp_reduce16_store(m, red[threadIdx.x >> 5],
                         w.partial + ((size_t)pair * w.src_rows + (size_t)(blockIdx.x * (NN_THREADS / 32) + (threadIdx.x >> 5))) * 16);
 }
 
 // The bracket of a large pair (one CTA per pair): its c members ordered by (squared distance, position), the first k' kept.
-// Publishes tau / idx_cut and writes the kept members' moments as row `(n + 31) / 32` of the pair's table.  Up to
+// Publishes tau / idx_cut and writes the kept members' moments as row `mom_rows(n)` of the pair's table.  Up to
 // FSEL_RANKED members (the normal case: a few dozen) every member's rank is counted directly and the kept ones are summed
 // in rank order; a larger bracket (many equal distances) is resolved by bisection on the key bits and summed in position
 // order by a sweep over all queries -- slower, deterministic either way.
 constexpr int SOLVE_THREADS = 512;
 constexpr int FSEL_RANKED = 2048;
 
-__global__ void __launch_bounds__(SOLVE_THREADS)
-fsel_resolve_kernel(IcpWorkspace w) {
-    const int pair = blockIdx.x;
+__device__ __forceinline__ void fsel_resolve_body(IcpWorkspace& w, int pair) {
     PairState* st = w.state + pair;
     const int n = st->n_src;
     if (st->done) return;
@@ -824,7 +848,7 @@ fsel_resolve_kernel(IcpWorkspace w) {
     __shared__ int s_byrank[FSEL_RANKED];
     __shared__ unsigned long long s_tau;
     __shared__ int s_cut;
-    double* row = w.partial + ((size_t)pair * w.src_rows + (size_t)((n + 31) / 32)) * 16;
+    double* row = w.partial + ((size_t)pair * w.src_rows + (size_t)mom_rows(n)) * 16;
     const FSel fs = w.fsel[pair];
     if (sel_is_small(n)) return;      // (selected by sel_small_kernel; solve_kernel does not read a bracket row for them)
     if (fs.all) {
@@ -963,17 +987,10 @@ __device__ __forceinline__ void sum_rows16(const double* __restrict__ rows, int 
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SOLVE_THREADS)
-solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
-    const int pair = blockIdx.x;
+// One ICP step of a pair from its table of moment rows (every thread of a CTA of SOLVE_THREADS): fixed-order sum, Kabsch,
+// T <- T_iter T, convergence test (utils/icp.py:113-128).
+__device__ __forceinline__ void solve_body(IcpWorkspace& w, int pair, double tolerance, int rows, double* sm, double* m) {
     PairState* st = w.state + pair;
-    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
-    if (st->done) return;
-    __shared__ double sm[SOLVE_THREADS];
-    __shared__ double m[16];
-    const int n = st->n_src;
-    // fused mode: one row per warp of the persistent nn kernel; otherwise one row per 32 queries
-    const int rows = rows_fixed > 0 ? vwarps_for(n) : (n + 31) / 32 + (sel_is_small(n) ? 0 : 1);      // (+ 1: the bracket row of fsel_resolve_kernel, large pairs)
     sum_rows16(w.partial + (size_t)pair * w.src_rows * 16, rows, sm, m);
     if (threadIdx.x == 0) {
         const GridParams& g = w.grid.params[pair];
@@ -998,6 +1015,38 @@ solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
             st->iters += 1;
         }
     }
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS)
+solve_kernel(IcpWorkspace w, double tolerance, int rows_fixed) {
+    const int pair = blockIdx.x;
+    PairState* st = w.state + pair;
+    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
+    if (st->done) return;
+    __shared__ double sm[SOLVE_THREADS];
+    __shared__ double m[16];
+    const int n = st->n_src;
+    // fused mode: one row per virtual warp of the persistent nn kernel; otherwise moments_kernel's rows
+    const int rows = rows_fixed > 0 ? vwarps_for(n) : mom_rows(n) + (sel_is_small(n) ? 0 : 1);      // (+ 1: the bracket row of fsel_resolve_body, large pairs)
+    solve_body(w, pair, tolerance, rows, sm, m);
+}
+
+// partial_set_size < 1, large pairs: the bracket's exact finish and the ICP step in one launch (both are one CTA per pair,
+// the second reads the row the first has just written).
+__global__ void __launch_bounds__(SOLVE_THREADS)
+resolve_solve_kernel(IcpWorkspace w, double tolerance) {
+    const int pair = blockIdx.x;
+    fsel_resolve_body(w, pair);
+    __threadfence();
+    __syncthreads();
+    PairState* st = w.state + pair;
+    if (threadIdx.x == 0) w.vw_counter[pair] = 0;      // the nn launch of this iteration has finished
+    if (st->done) return;
+    __shared__ double sm[SOLVE_THREADS];
+    __shared__ double m[16];
+    const int n = st->n_src;
+    const int rows = mom_rows(n) + (sel_is_small(n) ? 0 : 1);
+    solve_body(w, pair, tolerance, rows, sm, m);
 }
 
 // ---- moments of A and the final fit -----------------------------------------------------------------------
@@ -1238,10 +1287,10 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
                 for (int pass = 0; pass < FSEL_PASSES; pass++)
                     R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
             }
-            R3D_LAUNCH(moments_kernel, qgrid, NN_THREADS, 0, st, w);
-            if (w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(fsel_resolve_kernel, P, SOLVE_THREADS, 0, st, w);
+            R3D_LAUNCH(moments_kernel, dim3((w.max_src + MOM_TILE - 1) / MOM_TILE, P), NN_THREADS, 0, st, w);
         }
-        R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
+        if (!fused && w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(resolve_solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance);
+        else R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
     }
     R3D_LAUNCH(final_kernel, (P + 63) / 64, 64, 0, st, w, T_out, iters_out, mean_err_out);
     if ((last_idx || last_dist || last_keep) && prm.max_iterations > 0) {
