@@ -287,6 +287,9 @@ __device__ __forceinline__ void accumulate_pair(double (&m)[16], double ax, doub
     m[15] = dist;
 }
 
+// fp32 key of a squared distance for the top-fraction selection (monotone: rounded towards zero); see fsel_hist_kernel
+__device__ __forceinline__ uint32_t key32(double d2) { return __float_as_uint(__double2float_rz(d2)); }
+
 // ---- nearest neighbour ----------------------------------------------------------------------------
 // Persistent query kernel: grid (CTAs per pair, pairs); a task is 32 consecutive queries of the sorted source cloud.
 // Work is dealt to vwarps_for(n_src) "virtual warps" per pair (virtual warp u owns tasks u, u + nvw, ...), handed
@@ -330,7 +333,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int pair = blockIdx.y;
     __shared__ GridParams g;
     __shared__ double T[12], D[12];
-    __shared__ int s_n, s_done;
+    __shared__ int s_n, s_done, s_cutoff;
     // the grid's base pointers live in shared memory: the compiler would otherwise recompute these 64-bit
     // addresses inside every loop of the search
     __shared__ GridView s_view;
@@ -340,6 +343,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
         g = w.grid.params[pair];
         s_n = w.state[pair].n_src;
         s_done = w.state[pair].done;
+        s_cutoff = w.state[pair].cutoff;
         s_view = grid_view(w.grid, pair);
     }
     if (threadIdx.x < 12) {
@@ -364,6 +368,9 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const int nvw = vwarps_for(s_n);
     const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
+    // (selection of a large pair at partial_set_size < 1: see the epilogue of the task loop)
+    uint32_t* hist0 = (!FUSED && write_d2 == 2 && s_n > NN_SMALL_PAIR && s_cutoff < s_n)
+                          ? w.sel_hist + ((size_t)pair * FSEL_PASSES + 0) * SEL_BINS : nullptr;
     unsigned phase = 0;      // parity of the warp's staging mbarrier(s)
     if constexpr (IMPL == 1) {
         list_init(ssm[warp].list, v.pts);
@@ -466,6 +473,20 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
             R3D_STAT_MAX(13, clock64() - t_task);
 #endif
             const Best best = seed_wins ? seed : other;
+            if constexpr (!FUSED) {
+                // partial_set_size < 1, large pairs: the first histogram pass of the selection (top 11 bits of the fp32 key of
+                // every distance, fsel_hist_kernel) is counted here, where the distances are made: one pass over d2 and one
+                // launch per iteration less.  Warp-aggregated: the 32 distances of a task fall into a handful of bins.
+                if (hist0 != nullptr) {
+                    const bool mine = active && primary;
+                    const unsigned am = __ballot_sync(0xffffffffu, mine);
+                    if (mine) {
+                        const uint32_t bin = key32(best.d2) >> 21;
+                        const unsigned grp = __match_any_sync(am, bin);
+                        if ((grp & ((1u << lane) - 1u)) == 0u) atomicAdd(hist0 + bin, (uint32_t)__popc(grp));
+                    }
+                }
+            }
             if (active && primary) {
                 nn_pos[i] = best.pos;
                 if (!FUSED || write_d2) d2_out[i] = best.d2;
@@ -523,10 +544,51 @@ __host__ __device__ __forceinline__ int sel_bits(int pass) { return pass == 0 ? 
 // (distance, position) exactly, keeps the first k', publishes tau / idx_cut (kept() below) and adds their moments as one more
 // row.  Exact ties at the cutoff keep the lowest positions, as before; a bracket that holds many points (lattices: every
 // distance the same double) takes a slower, still exact route through fsel_resolve_kernel.
-__device__ __forceinline__ uint32_t key32(double d2) { return __float_as_uint(__double2float_rz(d2)); }
 
+// Which of the SEL_BINS counters of `gh` (global) holds rank k, and the rank left inside it: every thread of a CTA of 256 gets
+// the answer (8 bins per thread, block scan).  zero: the counters are also reset for the next iteration's selection.
+__device__ __forceinline__ void hist_pick256(uint32_t* gh, uint32_t k, bool zero, uint32_t* warp_tot /* [8] shared */,
+                                             uint32_t* s_out /* [2] shared */, uint32_t& bin, uint32_t& kk) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        c[j] = __ldcg(gh + threadIdx.x * 8 + j);
+        if (zero) gh[threadIdx.x * 8 + j] = 0;
+        tot += c[j];
+    }
+    uint32_t x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();      // (warp_tot / s_out may still be read from an earlier call)
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    uint32_t before = x - tot;
+    for (int wv = 0; wv < warp; wv++) before += warp_tot[wv];
+    if (k >= before && k < before + tot) {      // exactly one thread
+        uint32_t r = k - before;
+        int j = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            if (j == q && r >= c[q]) { r -= c[q]; j = q + 1; }
+        }
+        s_out[0] = (uint32_t)(threadIdx.x * 8 + j);
+        s_out[1] = r;
+    }
+    __syncthreads();
+    bin = s_out[0];
+    kk = s_out[1];
+}
+
+// The second (and last) histogram pass of a large pair's selection.  The FIRST pass -- the top 11 bits of every key -- is
+// counted by the nn kernel itself as it produces the distances (nn_query_kernel, `hist0`): every CTA here starts by reading
+// those 2048 counters and picking the bin of rank cutoff - 1 (the same answer in every CTA), counts the next 11 bits of the
+// keys inside that bin, and the last CTA to finish picks again, publishes the 22-bit bracket and resets both histograms.
 __global__ void __launch_bounds__(256)
-fsel_hist_kernel(IcpWorkspace w, int pass) {
+fsel_hist_kernel(IcpWorkspace w) {
     const int pair = blockIdx.y;
     const PairState* st = w.state + pair;
     const int n = st->n_src;
@@ -541,12 +603,15 @@ fsel_hist_kernel(IcpWorkspace w, int pass) {
     }
     __shared__ uint32_t hist[SEL_BINS];
     __shared__ uint32_t warp_tot[8];
+    __shared__ uint32_t s_pick[2];
     __shared__ int s_last;
     for (int k = threadIdx.x; k < SEL_BINS; k += 256) hist[k] = 0;
-    __syncthreads();
+    uint32_t* gh0 = w.sel_hist + ((size_t)pair * FSEL_PASSES + 0) * SEL_BINS;
+    uint32_t* gh = w.sel_hist + ((size_t)pair * FSEL_PASSES + 1) * SEL_BINS;
+    uint32_t prefix, k1;
+    hist_pick256(gh0, (uint32_t)(cutoff - 1), false, warp_tot, s_pick, prefix, k1);      // (ends with a barrier: hist[] is zero for all)
     const double* d2 = w.d2 + (size_t)pair * w.max_src;
-    const uint32_t prefix = pass == 0 ? 0u : fs->prefix;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 #pragma unroll 4
     for (int r = 0; r < SEL_TILE / 256; r++) {
         const int i = base + r * 256 + threadIdx.x;
@@ -554,65 +619,41 @@ fsel_hist_kernel(IcpWorkspace w, int pass) {
         uint32_t d = 0;
         if (i < n) {
             const uint32_t key = key32(d2[i]);
-            in = pass == 0 || (key >> 21) == prefix;
-            d = pass == 0 ? key >> 21 : (key >> 10) & 2047u;
+            in = (key >> 21) == prefix;
+            d = (key >> 10) & 2047u;
         }
         const unsigned active = __ballot_sync(0xffffffffu, in);
         if (active == 0u) continue;
         if (in) {
-            // warp-aggregated increment among the lanes that match (the first pass puts every key into a few bins)
+            // warp-aggregated increment among the lanes that match
             const unsigned grp = __match_any_sync(active, d);
             if ((grp & ((1u << lane) - 1u)) == 0) atomicAdd(&hist[d], (uint32_t)__popc(grp));
         }
     }
     __syncthreads();
-    uint32_t* gh = w.sel_hist + ((size_t)pair * FSEL_PASSES + pass) * SEL_BINS;
     for (int k = threadIdx.x; k < SEL_BINS; k += 256) {
         const uint32_t c = hist[k];
         if (c) atomicAdd(gh + k, c);
     }
-    // the last CTA of this pair to get here picks the bin that holds rank k
+    // the last CTA of this pair to get here picks the bin that holds the rank
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t ctas = (uint32_t)((n + SEL_TILE - 1) / SEL_TILE);
-        s_last = atomicAdd(w.fsel_done + pair * FSEL_PASSES + pass, 1u) == ctas - 1u;
+        s_last = atomicAdd(w.fsel_done + pair, 1u) == ctas - 1u;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const uint32_t k = pass == 0 ? (uint32_t)(cutoff - 1) : fs->k;
-    uint32_t c[8], tot = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        c[j] = __ldcg(gh + threadIdx.x * 8 + j);
-        gh[threadIdx.x * 8 + j] = 0;      // ready for the next iteration's selection
-        tot += c[j];
-    }
-    uint32_t x = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    if (lane == 31) warp_tot[warp] = x;
-    __syncthreads();
-    uint32_t before = x - tot;
-    for (int wv = 0; wv < warp; wv++) before += warp_tot[wv];
-    if (k >= before && k < before + tot) {      // exactly one thread
-        uint32_t kk = k - before;
-        int j = 0;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            if (j == q && kk >= c[q]) { kk -= c[q]; j = q + 1; }
-        }
-        fs->prefix = (prefix << 11) | (uint32_t)(threadIdx.x * 8 + j);
-        fs->k = kk;
-        fs->all = 0u;
-    }
+    uint32_t bin1, k2;
+    hist_pick256(gh, k1, true, warp_tot, s_pick, bin1, k2);
+    for (int k = threadIdx.x; k < SEL_BINS; k += 256) gh0[k] = 0;      // every CTA of the pair has read it: ready for the next nn launch
     if (threadIdx.x == 0) {
-        w.fsel_done[pair * FSEL_PASSES + pass] = 0u;
-        if (pass == FSEL_PASSES - 1) w.cand_n[pair] = 0u;      // (fsel_moments_kernel fills the list next)
+        fs->prefix = (prefix << 11) | bin1;
+        fs->k = k2;
+        fs->all = 0u;
+        w.fsel_done[pair] = 0u;
+        w.cand_n[pair] = 0u;      // (moments_kernel fills the list next)
     }
 }
 
@@ -1274,7 +1315,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
         if (sharded) R3D_CUDA(cudaMemsetAsync(w.partial, 0, shard_doubles * sizeof(double), st));
         {
             NnTimer timer(st);
-            rc = launch_nn(w, it > 0, fused, fused ? want_d2 : 1, st);
+            rc = launch_nn(w, it > 0, fused, fused ? want_d2 : 2, st);      // (2: distances are written AND their first selection histogram counted)
             if (rc != R3D_OK) return rc;
         }
         if (sharded) {
@@ -1283,10 +1324,7 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
         }
         if (!fused) {
             R3D_LAUNCH(sel_small_kernel, P, 1024, 0, st, w);
-            if (w.max_src > NN_SMALL_PAIR) {
-                for (int pass = 0; pass < FSEL_PASSES; pass++)
-                    R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w, pass);
-            }
+            if (w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w);
             R3D_LAUNCH(moments_kernel, dim3((w.max_src + MOM_TILE - 1) / MOM_TILE, P), NN_THREADS, 0, st, w);
         }
         if (!fused && w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(resolve_solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance);
