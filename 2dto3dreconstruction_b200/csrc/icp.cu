@@ -8,11 +8,13 @@
 //                    the previous neighbour and skip the search altogether when the neighbour
 //                    provably cannot change.  With partial_set_size == 1 the 16 Kabsch moments are
 //                    reduced in the same kernel.
-//   sel_hist/pick    (partial < 1) radix-select of the cutoff-th smallest squared distance
-//                    = np.argpartition(distances, cutoff-1)[:cutoff], utils/icp.py:109-110
-//   moments_kernel   (partial < 1) moments over the kept correspondences
-//   solve_kernel     fixed-order sum of the per-CTA partials, 3x3 Kabsch (utils/icp.py:22-55),
-//                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126)
+//   (partial < 1)    selection of the cutoff-th smallest squared distance = np.argpartition(distances, cutoff-1)[:cutoff],
+//                    utils/icp.py:109-110: the first histogram pass is counted inside nn_query_kernel, fsel_hist_kernel
+//                    counts the second and brackets the cutoff (small pairs: sel_small_kernel, one launch)
+//   moments_kernel   (partial < 1) moments over the kept correspondences, list of the bracket's members
+//   solve_kernel     fixed-order sum of the partial rows, 3x3 Kabsch (utils/icp.py:22-55),
+//                    T_cum <- T_iter * T_cum, mean error, |prev - mean| < tol test (icp.py:123-126);
+//                    resolve_solve_kernel (partial < 1, large pairs): the bracket's exact finish, then the same step
 // After the loop, final_kernel reproduces utils/icp.py:131 best_fit_transform(A, src) from the
 // second moments of A (src is the affine image T_cum * A, so H = C_A * M^T in closed form).
 #include <type_traits>
@@ -116,7 +118,7 @@ static size_t icp_workspace_layout(IcpWorkspace& w, Arena& a, int n_pairs, int m
     w.shard_world = 1;
     w.src_tiles = (max_src + NN_THREADS - 1) / NN_THREADS;      // CTAs per pair
     // rows of `partial`: one per warp of the widest launch (whole CTAs, so round up per CTA)
-    w.src_rows = w.src_tiles * (NN_THREADS / 32) + 1;      // (+ 1: the bracket row of fsel_resolve_kernel)
+    w.src_rows = w.src_tiles * (NN_THREADS / 32) + 1;      // (+ 1: the bracket row of fsel_resolve_body)
     if (w.src_rows < vwarps_for(max_src)) w.src_rows = vwarps_for(max_src);
     const size_t P = (size_t)n_pairs;
     w.state = a.take<PairState>(P);
@@ -537,13 +539,13 @@ __host__ __device__ __forceinline__ int sel_bits(int pass) { return pass == 0 ? 
 // ---- selection of a large pair: two histogram passes on an fp32 key, a bracket, an exact finish ------------------
 // The k-th smallest of n squared distances (n up to millions) used to take six histogram + six pick launches on the 64-bit
 // keys.  Now: key32 = bits of the distance rounded TOWARDS ZERO to fp32 -- a monotone map, so the k-th smallest double has the
-// k-th smallest key32 -- and two histogram passes (11 bits each; the last CTA of a pass to finish scans the 2048 bins and
-// picks, no separate launch) leave a BRACKET: the distances whose key32 shares the 22 leading bits of the k-th one's, a
-// relative width of 2^-13, a few dozen of 276 k.  Everything below the bracket is kept for certain and its moments are summed
-// by fsel_moments_kernel in the same pass that lists the bracket's members; fsel_resolve_kernel then orders the members by
-// (distance, position) exactly, keeps the first k', publishes tau / idx_cut (kept() below) and adds their moments as one more
-// row.  Exact ties at the cutoff keep the lowest positions, as before; a bracket that holds many points (lattices: every
-// distance the same double) takes a slower, still exact route through fsel_resolve_kernel.
+// k-th smallest key32 -- and two histogram passes (11 bits each; the first counted by the nn kernel, the second by
+// fsel_hist_kernel, whose last CTA picks) leave a BRACKET: the distances whose key32 shares the 22 leading bits of the k-th
+// one's, a relative width of 2^-13, a few dozen of 276 k.  Everything below the bracket is kept for certain and its moments are
+// summed by moments_kernel in the same pass that lists the bracket's members; fsel_resolve_body (resolve_solve_kernel) then
+// orders the members by (distance, position) exactly, keeps the first k', publishes tau / idx_cut (kept() below) and adds their
+// moments as one more row.  Exact ties at the cutoff keep the lowest positions, as before; a bracket that holds many points
+// (lattices: every distance the same double) takes a slower, still exact route through fsel_resolve_body.
 
 // Which of the SEL_BINS counters of `gh` (global) holds rank k, and the rank left inside it: every thread of a CTA of 256 gets
 // the answer (8 bins per thread, block scan).  zero: the counters are also reset for the next iteration's selection.
@@ -805,7 +807,7 @@ __device__ __forceinline__ bool kept(double d2, int i, double tau, int idx_cut) 
 // query per thread and a row per 32 queries made the reductions -- not the 76 bytes per correspondence -- the kernel's cost, and
 // gave solve_kernel four times the rows to add.)  Small pairs: tau / idx_cut are final (sel_small_kernel).  Large pairs:
 // everything below the bracket of the k-th smallest distance is kept and summed here; the bracket's members are listed for
-// fsel_resolve_kernel; everything above is dropped.
+// fsel_resolve_body; everything above is dropped.
 constexpr int MOM_PT = 4;
 constexpr int MOM_TILE = NN_THREADS * MOM_PT;
 __host__ __device__ __forceinline__ int mom_rows(int n_src) { return ((n_src + MOM_TILE - 1) / MOM_TILE) * (NN_THREADS / 32); }
