@@ -180,8 +180,12 @@ __device__ inline void kabsch_rotation(const double Hin[9], double R[9]) {
 #pragma unroll
         for (int j = 0; j < 3; j++) { G[i][j] = Hin[i * 3 + j]; V[i][j] = (i == j) ? 1.0 : 0.0; }
 
+    // (The rotation is written with one square root, one division and one reciprocal square root -- t = tan of the Jacobi
+    // angle as 2 gamma sgn(d) / (|d| + sqrt(d^2 + 4 gamma^2)), d = beta - alpha -- and the size tests on squares: this loop is a
+    // single thread's dependent chain on the critical path of every ICP iteration, and fp64 sqrt / div are 25-40 instructions
+    // each.  Same angles as the textbook zeta form up to rounding.)
     for (int sweep = 0; sweep < 30; sweep++) {
-        double off = 0.0;
+        bool rotated = false;
 #pragma unroll
         for (int pq = 0; pq < 3; pq++) {
             const int p = (pq == 2) ? 1 : 0;
@@ -193,13 +197,14 @@ __device__ inline void kabsch_rotation(const double Hin[9], double R[9]) {
                 beta += G[i][q] * G[i][q];
                 gamma += G[i][p] * G[i][q];
             }
-            double lim = 1e-30 + 1e-16 * sqrt(alpha * beta);
-            if (fabs(gamma) > lim) {
-                off = fmax(off, fabs(gamma) / (sqrt(alpha * beta) + 1e-300));
-                double zeta = (beta - alpha) / (2.0 * gamma);
-                double t = ((zeta >= 0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / sqrt(1.0 + t * t);
-                double s = c * t;
+            const double ab = alpha * beta, g2 = gamma * gamma;
+            // rotate while |gamma| > 1e-30 + 1e-16 sqrt(alpha beta); converged once every |gamma| <= 1e-15 sqrt(alpha beta)
+            if (g2 > 1e-60 + 1e-32 * ab) {
+                rotated = rotated || (g2 >= 1e-30 * ab);
+                const double d = beta - alpha;
+                const double t = ((d >= 0) ? 2.0 * gamma : -2.0 * gamma) / (fabs(d) + sqrt(d * d + 4.0 * g2));
+                const double c = rsqrt(1.0 + t * t);
+                const double s = c * t;
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     double gp = G[i][p], gq = G[i][q];
@@ -211,7 +216,7 @@ __device__ inline void kabsch_rotation(const double Hin[9], double R[9]) {
                 }
             }
         }
-        if (off < 1e-15) break;
+        if (!rotated) break;
     }
     // singular values = column norms of G; order descending
     double sv[3];
