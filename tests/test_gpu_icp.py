@@ -142,6 +142,40 @@ def test_batch_matches_single_and_is_deterministic():
         assert_transform_parity(T, Tr, O.scene_extent(clouds[p][1]), "pair %d" % p, 1e-7, 1e-8)
 
 
+@pytest.mark.parametrize("partial", [0.7, 1.0])
+def test_mixed_batch_of_a_large_and_a_small_pair(partial):
+    """One pair above the 32 k points that switch a pair to the multi-CTA selection (first histogram pass counted inside the nn
+    kernel, bracket, resolve + solve in one launch) and one below (one-launch selection, four queries per task) in the SAME batch:
+    each must come out exactly as it does alone -- per-pair results do not depend on what else is in the launch."""
+    ops = sub("ops")
+    C = sub("_capi")
+    a, b = O.synth_depth_pair(7)
+    big = (O.depth_to_voxel_ld(a[:, :320].copy()), O.depth_to_voxel_ld(b[:, :320].copy()))
+    fa = np.zeros((480, 640), np.uint16)
+    fb = np.zeros((480, 640), np.uint16)
+    fa[100:180, 200:300] = a[100:180, 200:300]
+    fb[100:180, 200:300] = b[100:180, 200:300]
+    small = (O.depth_to_voxel_ld(fa), O.depth_to_voxel_ld(fb))
+    assert len(big[0]) > 32768 > len(small[0]) > 1000
+    kw = dict(max_iterations=12, tolerance=0.0, partial_set_size=partial)
+
+    def run(pairs):
+        ns, ms = [len(p[0]) for p in pairs], [len(p[1]) for p in pairs]
+        s = ops.pack_xyzw(C.to_device(np.concatenate([p[0] for p in pairs])))
+        d = ops.pack_xyzw(C.to_device(np.concatenate([p[1] for p in pairs])))
+        r = ops.icp_batch(s, ops._offsets(ns), d, ops._offsets(ms), len(pairs), max(ns), max(ms), **kw)
+        return r["T"].cpu().numpy(), r["mean_err"].cpu().numpy()
+
+    Tb, eb = run([big, small])
+    for k, pair in enumerate((big, small)):
+        T1, e1 = run([pair])
+        assert np.array_equal(Tb[k], T1[0]) and eb[k] == e1[0], "pair %d changes with the batch" % k
+        Tr, _, _ = O.icp(pair[0], pair[1], **kw)
+        # (quantised depth: exact distance ties are real, the KD-tree breaks them differently -- north_star's tolerance, as in
+        # test_full_density_pair)
+        assert_transform_parity(Tb[k], Tr, O.scene_extent(pair[1]), "pair %d" % k)
+
+
 def test_zero_iterations_and_identity():
     icp = sub("utils.icp")
     rng = np.random.default_rng(0)
