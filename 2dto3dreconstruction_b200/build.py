@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 ] + (["-DR3D_NN_MIN_CTAS=" + os.environ["R3D_NN_MIN_CTAS"]] if os.environ.get("R3D_NN_MIN_CTAS") else []) \
   + (["-DR3D_LEAN_MIN_CTAS=" + os.environ["R3D_LEAN_MIN_CTAS"]] if os.environ.get("R3D_LEAN_MIN_CTAS") else []) \
   + (["-DR3D_NN_STATS"] if os.environ.get("R3D_NN_STATS") else []) \
-  + ["-D%s=%s" % (k, os.environ[k]) for k in ("R3D_LEAN_FLUSH", "R3D_LEAN_RCAP0", "R3D_LEAN_TMA", "R3D_LEAN_WIN", "R3D_LEAN_ROW_SEGS_MAX", "R3D_LEAN_BLOCKS_MAX", "R3D_NN_MID_PAIR", "R3D_BP_V8", "R3D_BP_ONEPASS", "R3D_LOAD256", "R3D_STORE256", "R3D_BP_MIN_CTAS", "R3D_NN_SMALL_QPT", "R3D_NN_PREFETCH", "R3D_RS3_TILE", "R3D_RS3_MINB") if os.environ.get(k)]
+  + ["-D%s=%s" % (k, os.environ[k]) for k in ("R3D_LEAN_FLUSH", "R3D_SEL_SMALL_MAX", "R3D_LEAN_RCAP0", "R3D_LEAN_TMA", "R3D_LEAN_WIN", "R3D_LEAN_ROW_SEGS_MAX", "R3D_LEAN_BLOCKS_MAX", "R3D_NN_MID_PAIR", "R3D_BP_V8", "R3D_BP_ONEPASS", "R3D_LOAD256", "R3D_STORE256", "R3D_BP_MIN_CTAS", "R3D_NN_SMALL_QPT", "R3D_NN_PREFETCH", "R3D_RS3_TILE", "R3D_RS3_MINB") if os.environ.get(k)]
 
 
 def _nvcc():

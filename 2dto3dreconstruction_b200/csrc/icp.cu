@@ -44,6 +44,14 @@ constexpr int NN_VWARPS_BIG_FROM = 1 << 19;      // still fill the GPU.  A funct
 // function of the pair alone.  (8 / 4 / 2 queries per task on the sofa pair: 149 / 140 / 164 us per launch at
 // partial_set_size 1.0, 203 / 163 / 149 us at 0.7.)
 constexpr int NN_SMALL_PAIR = 1 << 15;
+// Pairs of at most this many source points take the one-CTA selection (sel_small_kernel: six 64-bit histogram passes back to
+// back); larger ones the bracket selection (first pass in the nn kernel, fsel_hist_kernel, moments_kernel, resolve_solve_kernel).
+// (0 = every pair through the bracket selection: correct, and 12 % slower on the reference's 13 k-point pairs -- 16.3 against
+// 14.6 ms for 100 iterations -- whose whole key set a single CTA walks in a few microseconds.)
+#ifndef R3D_SEL_SMALL_MAX
+#define R3D_SEL_SMALL_MAX (1 << 15)
+#endif
+constexpr int SEL_SMALL_MAX = R3D_SEL_SMALL_MAX;
 #ifndef R3D_NN_MID_PAIR
 #define R3D_NN_MID_PAIR 0
 #endif
@@ -371,7 +379,7 @@ nn_query_kernel(IcpWorkspace w, int write_d2, LeanTuning tune) {
     const float slack_max = tune.slack_max_frac * (float)g.cell;
     int* vw_counter = w.vw_counter + pair;
     // (selection of a large pair at partial_set_size < 1: see the epilogue of the task loop)
-    uint32_t* hist0 = (!FUSED && write_d2 == 2 && s_n > NN_SMALL_PAIR && s_cutoff < s_n)
+    uint32_t* hist0 = (!FUSED && write_d2 == 2 && s_n > SEL_SMALL_MAX && s_cutoff < s_n)
                           ? w.sel_hist + ((size_t)pair * FSEL_PASSES + 0) * SEL_BINS : nullptr;
     unsigned phase = 0;      // parity of the warp's staging mbarrier(s)
     if constexpr (IMPL == 1) {
@@ -594,7 +602,7 @@ fsel_hist_kernel(IcpWorkspace w) {
     const int pair = blockIdx.y;
     const PairState* st = w.state + pair;
     const int n = st->n_src;
-    if (st->done || n <= NN_SMALL_PAIR) return;
+    if (st->done || n <= SEL_SMALL_MAX) return;
     const int base = blockIdx.x * SEL_TILE;
     if (base >= n) return;
     FSel* fs = w.fsel + pair;
@@ -765,7 +773,7 @@ __device__ __forceinline__ void sel_pick_step(IcpWorkspace& w, int pair, int pas
 
 // Pairs of at most NN_SMALL_PAIR source points are selected by sel_small_kernel below, the others by the
 // multi-CTA histogram passes.
-__device__ __forceinline__ bool sel_is_small(int n_src) { return n_src <= NN_SMALL_PAIR; }
+__device__ __forceinline__ bool sel_is_small(int n_src) { return n_src <= SEL_SMALL_MAX; }
 
 // The whole selection of a small pair in one launch: one CTA, the six histogram + pick steps back to back on a
 // shared-memory histogram (the keys, at most 256 KB, stay in L1/L2).  For the reference's own cloud sizes the twelve
@@ -1325,11 +1333,11 @@ int icp_run(IcpWorkspace& w, const Point4* src, const int32_t* src_off, const Po
             if (shard->exchange(shard->ctx, w.partial, shard_doubles, (void*)st) != 0) return R3D_ERR_INVALID;
         }
         if (!fused) {
-            R3D_LAUNCH(sel_small_kernel, P, 1024, 0, st, w);
-            if (w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w);
+            if (SEL_SMALL_MAX > 0) R3D_LAUNCH(sel_small_kernel, P, 1024, 0, st, w);
+            if (w.max_src > SEL_SMALL_MAX) R3D_LAUNCH(fsel_hist_kernel, dim3((w.max_src + SEL_TILE - 1) / SEL_TILE, P), 256, 0, st, w);
             R3D_LAUNCH(moments_kernel, dim3((w.max_src + MOM_TILE - 1) / MOM_TILE, P), NN_THREADS, 0, st, w);
         }
-        if (!fused && w.max_src > NN_SMALL_PAIR) R3D_LAUNCH(resolve_solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance);
+        if (!fused && w.max_src > SEL_SMALL_MAX) R3D_LAUNCH(resolve_solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance);
         else R3D_LAUNCH(solve_kernel, P, SOLVE_THREADS, 0, st, w, prm.tolerance, fused ? 1 : 0);
     }
     R3D_LAUNCH(final_kernel, (P + 63) / 64, 64, 0, st, w, T_out, iters_out, mean_err_out);
