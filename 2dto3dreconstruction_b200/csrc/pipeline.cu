@@ -112,6 +112,16 @@ int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool hos
     ppc = default_ppc(ppc);
     if (ppc > n_pairs) ppc = n_pairs;
     n_streams = default_streams(n_streams);
+    {
+        // A handful of chunks that do not divide over the streams leave one stream a whole chunk behind the others (128 pairs in
+        // chunks of 32 on three streams: 2 + 1 + 1): cut them a little smaller instead (six chunks of 22).  Never larger than the
+        // caller's chunk (the workspace was sized for it); per-pair results do not depend on the chunking.
+        int n_chunks = (n_pairs + ppc - 1) / ppc;
+        if (n_chunks > n_streams && n_chunks < 4 * n_streams && n_chunks % n_streams != 0) {
+            n_chunks = ((n_chunks + n_streams - 1) / n_streams) * n_streams;
+            ppc = (n_pairs + n_chunks - 1) / n_chunks;
+        }
+    }
     const size_t hw = (size_t)h * w;
     if ((size_t)ppc * hw > 0x7fffffffull) return R3D_ERR_INVALID;
 
