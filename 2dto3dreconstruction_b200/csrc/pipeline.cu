@@ -116,8 +116,13 @@ int register_impl(const uint16_t* depth_src, const uint16_t* depth_dst, bool hos
         // A handful of chunks that do not divide over the streams leave one stream a whole chunk behind the others (128 pairs in
         // chunks of 32 on three streams: 2 + 1 + 1): cut them a little smaller instead (six chunks of 22).  Never larger than the
         // caller's chunk (the workspace was sized for it); per-pair results do not depend on the chunking.
+        // Fewer chunks than streams (a batch of 32 in one chunk): one chunk per stream, so that the one-CTA-per-pair steps of a
+        // chunk overlap the searches of the others (32 pairs: 1038 -> 1233 pairs/s; 64 pairs: no change).
         int n_chunks = (n_pairs + ppc - 1) / ppc;
-        if (n_chunks > n_streams && n_chunks < 4 * n_streams && n_chunks % n_streams != 0) {
+        if (n_chunks < n_streams && n_pairs >= 4 * n_streams) {
+            n_chunks = n_streams;
+            ppc = (n_pairs + n_chunks - 1) / n_chunks;
+        } else if (n_chunks > n_streams && n_chunks < 4 * n_streams && n_chunks % n_streams != 0) {
             n_chunks = ((n_chunks + n_streams - 1) / n_streams) * n_streams;
             ppc = (n_pairs + n_chunks - 1) / n_chunks;
         }
