@@ -244,8 +244,10 @@ int r3d_voxel_downsample(const double* xyz, int64_t n, double voxel_size, double
  *   reconstruct_rgbd.py:48) for the synthetic-depth configuration.
  *   depth_src / depth_dst: uint16 [n_pairs, height, width] (device, or pinned host for the
  *   *_host variant, which stages chunks through the workspace with copies overlapped).
- *   n_src_out / n_dst_out: int32[n_pairs] cloud sizes.  pairs_per_chunk: pairs processed
- *   per launch group (<=0: default).
+ *   n_src_out / n_dst_out: int32[n_pairs] cloud sizes.  pairs_per_chunk: the LARGEST number of
+ *   pairs processed per launch group (<=0: default); a batch that gives fewer chunks than
+ *   streams, or a handful that do not divide over them, is cut into smaller, equal chunks
+ *   (the workspace is sized for the value given; per-pair results do not depend on it).
  *   The *_host variant synchronises before returning; outputs are HOST pointers there.
  * ------------------------------------------------------------------------------------ */
 size_t r3d_register_workspace_bytes(int n_pairs, int pairs_per_chunk, int height, int width, int n_streams);
